@@ -1,0 +1,72 @@
+/* ORACLE (test infrastructure, NOT product code) -- public entry points of liborc.so (CPU restatement).
+ * Loaded with ctypes by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs ONLY.
+ * Every function cites the reference interface it restates; see the .c files.
+ *
+ * Conventions:  field elements = 4 x u64 LE limbs, Montgomery form (gnark-crypto memory
+ * layout); hashes / Merkle nodes = 32-byte big-endian canonical; G1 affine = X||Y (8 u64), G2 affine =
+ * X.A0||X.A1||Y.A0||Y.A1 (16 u64); infinity = all zero.
+ */
+#ifndef ORC_H
+#define ORC_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int  orc_num_threads(void);
+
+/* field helpers (which: 0 = Fp, 1 = Fr) */
+void orc_to_mont(uint64_t *inout, size_t n, int which);
+void orc_from_mont(uint64_t *inout, size_t n, int which);
+void orc_fr_mul_batch(const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+
+/* curve */
+void orc_g1_fixed_base(const uint64_t *scalars_plain, size_t n, uint64_t *out_aff, int threads);   /* k_i * G1 */
+void orc_g2_fixed_base(const uint64_t *scalars_plain, size_t n, uint64_t *out_aff, int threads);   /* k_i * G2 */
+void orc_g1_msm(const uint64_t *pts, const uint64_t *scalars_mont, size_t n, uint64_t *out_aff, int threads);
+void orc_g2_msm(const uint64_t *pts, const uint64_t *scalars_mont, size_t n, uint64_t *out_aff, int threads);
+void orc_g1_add(const uint64_t *p, const uint64_t *q, uint64_t *out_aff);
+void orc_g1_scalar_mul(const uint64_t *p, const uint64_t *k_plain, uint64_t *out_aff);
+void orc_g2_add(const uint64_t *p, const uint64_t *q, uint64_t *out_aff);
+void orc_g2_scalar_mul(const uint64_t *p, const uint64_t *k_plain, uint64_t *out_aff);
+int  orc_g1_on_curve(const uint64_t *p);
+int  orc_g2_on_curve(const uint64_t *p);
+
+/* NTT (gnark-crypto fft.Domain conventions) */
+void orc_ntt(uint64_t *data_mont, int logn, int inverse, int dit, int coset, int threads);
+void orc_compute_h(const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t m, int logn, uint64_t *out_h, int threads);
+
+/* Poseidon / Merkle */
+void orc_poseidon_set_out_lane(int lane);
+int  orc_poseidon_get_out_lane(void);
+void orc_poseidon_constants(int t, uint64_t *rc_mont /* (8+RP)*t*4 */, uint64_t *mds_mont /* t*t*4 */, int *rounds_p);
+void orc_poseidon_permute(uint64_t *state_mont, int t);
+void orc_poseidon_hash(const uint64_t *in_mont, size_t n_in, uint64_t *out_mont);
+void orc_poseidon_hash_be(const uint8_t *in_be, size_t n_in, uint8_t *out_be);
+void orc_poseidon_node_batch(const uint8_t *pairs_be, size_t count, uint8_t *out_be, int threads);
+size_t orc_merkle_level_len(size_t capacity, int level);
+size_t orc_merkle_nodes_total(size_t capacity, int depth);
+void orc_merkle_build(const uint8_t *leaves, const uint64_t *dirty, size_t capacity, int depth, const uint8_t *nil_leaf,
+                      uint8_t *out_nodes, uint8_t *out_root, int threads);
+void orc_merkle_proofs(const uint8_t *leaves, const uint64_t *dirty, const uint8_t *nodes, size_t capacity, int depth,
+                       const uint8_t *nil_leaf, const uint32_t *keys, size_t nkeys, uint8_t *out);
+void orc_account_leaves(const uint8_t *ids_be, const uint8_t *totals_be, const uint64_t *flat_assets, size_t n_accounts,
+                        int tier, uint8_t *out_be, int threads);
+
+/* Groth16 prove (gnark v0.10 backend/groth16/bn254/prove.go restated) */
+typedef struct {
+    uint64_t n_a, n_b, n_k, n_z, n_ck;        /* point counts: A, B1(=B2), K, Z (= domain-1), commitment basis */
+    const uint64_t *A, *B1, *K, *Z, *B2;      /* affine, Montgomery */
+    const uint64_t *ck_basis, *ck_basis_exp_sigma;
+    const uint64_t *alpha1, *beta1, *delta1, *beta2, *delta2;
+    int log_n;                                /* domain size */
+} orc_pk;
+int orc_groth16_prove(const orc_pk *pk, const uint64_t *wires_a, const uint64_t *wires_b, const uint64_t *wires_k,
+                      const uint64_t *committed, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_constraints,
+                      const uint64_t *r_plain, const uint64_t *s_plain, uint8_t *out_proof388, int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,126 @@
+"""Pin the Python oracle against every known answer available for the hot path:
+  * the reference's only byte-level fixture: src/verifier/config/user_config.json (12 empty-subtree node hashes);
+  * circomlib / go-iden3-crypto published Poseidon vectors (the parameter set the fork uses);
+  * EIP-196 / EIP-197 BN254 vectors for the curve arithmetic.
+The fixture is copied (data only) to tests/golden/user_config_proof.json by tests/golden/make_golden.py."""
+import base64
+import json
+import os
+
+import bn254 as bn
+import merkle
+import poseidon as ps
+from bn254 import FP2, G1_GEN, G2_GEN, P, R
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_poseidon_published_vectors_lane0():
+    # circomlibjs test/poseidon.js and go-iden3-crypto poseidon_test.go
+    assert ps.poseidon([1, 2], 0) == 0x115cc0f5e7d690413df64c6b9662e9cf2a3617f2743245519e19607a4417189a
+    assert ps.poseidon([1, 2, 3, 4], 0) == 0x299c867db6c1fdd79dcefa40e4510b9837e60ebb1ce0663dbaa525df65250465
+    assert ps.poseidon([1], 0) == 18586133768512220936620570745912940619677854269274689475585506675881198879027
+    assert ps.poseidon([1, 2, 0, 0, 0], 0) == 1018317224307729531995786483840663576608797660851238720571059489595066344487
+    assert ps.poseidon([1, 2, 0, 0, 0, 0], 0) == 15336558801450556532856248569924170992202208561737609669134139141992924267169
+    assert ps.poseidon([3, 4, 0, 0, 0], 0) == 5811595552068139067952687508729883632420015185677766880877743348592482390548
+    assert ps.poseidon([3, 4, 0, 0, 0, 0], 0) == 12263118664590987767234828103155242843640892839966517009184493198782366909018
+    assert ps.poseidon([1, 2, 3, 4, 5, 6], 0) == 20400040500897583745843009878988256314335038853985262692600694741116813247201
+
+
+def test_poseidon_constants_t3():
+    rc, mds = ps.constants(3)
+    assert rc[0] == 0x0ee9a592ba9a9518d05986d656f40c2114c4993c11bb29938d21d47304cd8e6e
+    assert mds[0][0] == 0x109b7f411ba0e4c9b2b70caf5c36a7b194be7c11ad24378bfedb68592ba8118b
+
+
+def test_reference_fixture_node_hash_chain():
+    """user_config.json:58-70 -- levels 15..27 are the empty-subtree chain: next = H(p, p), output lane 1."""
+    fx = json.load(open(os.path.join(GOLDEN, "user_config_proof.json")))
+    pr = [base64.b64decode(x) for x in fx["Proof"]]
+    assert len(pr) == 28
+    hits = 0
+    for i in range(15, 27):
+        assert ps.node_hash(pr[i], pr[i], out_lane=1) == pr[i + 1]
+        assert ps.node_hash(pr[i], pr[i], out_lane=0) != pr[i + 1]
+        hits += 1
+    assert hits == 12
+    assert ps.OUT_LANE == 1
+
+
+def test_hasher_wrapper_semantics():
+    h = ps.PoseidonHasher()
+    h.write(b"\x00")           # zero index encodes as []byte{0} (witness.go:185-192)
+    h.write(b"")               # big.Int(0).Bytes() is the empty slice (utils.go:748)
+    assert h.sum(b"xy")[:2] == b"xy"
+    assert h.data == []        # Sum clears pending elements
+    h.write((5).to_bytes(32, "big")); h.write(b"\x07")
+    assert h.sum() == ps.poseidon_bytes([b"\x05", b"\x07"])
+    try:
+        h.write(R.to_bytes(32, "big"))
+        assert False
+    except ValueError:
+        pass
+
+
+def test_wide_chaining_structure():
+    ins = list(range(1, 30))
+    st = ps.permute([0] + ins[:12])
+    st = ps.permute([st[0]] + ins[12:24])
+    st = ps.permute([st[0]] + ins[24:29])
+    assert ps.poseidon(ins, 0) == st[0] and ps.poseidon(ins, 1) == st[1]
+    # exactly 12 inputs: one full-width permutation, no trailing chunk
+    assert ps.poseidon(ins[:12], 0) == ps.permute([0] + ins[:12])[0]
+    assert ps.poseidon(ins[:24], 1) == ps.permute([ps.permute([0] + ins[:12])[0]] + ins[12:24])[1]
+
+
+def test_bn254_vectors():
+    two_g = (1368015179489954701390400359078579693043519447331113978918064868415326638035,
+             9918110051302171585080402603319702774565515993150576347155970296011118125764)
+    assert bn.pt_add(G1_GEN, G1_GEN) == two_g == bn.pt_mul(G1_GEN, 2)
+    assert bn.is_on_curve(G2_GEN, FP2) and bn.is_on_curve(two_g)
+    assert bn.pt_mul(G1_GEN, R) is None and bn.pt_mul(G2_GEN, R, FP2) is None
+    assert bn.pt_mul(G1_GEN, R - 1) == bn.pt_neg(G1_GEN)
+    assert pow(5, (R - 1) >> 28, R) == bn.FR_ROOT_2_28 and pow(bn.FR_ROOT_2_28, 1 << 27, R) == R - 1
+    assert P % 4 == 3
+
+
+def test_point_codecs_roundtrip():
+    for k in (1, 2, 7, 12345678901234567890):
+        p1 = bn.pt_mul(G1_GEN, k); p2 = bn.pt_mul(G2_GEN, k, FP2)
+        assert bn.g1_from_bytes(bn.g1_raw_bytes(p1)) == p1 and bn.g1_from_bytes(bn.g1_compressed_bytes(p1)) == p1
+        assert bn.g2_from_bytes(bn.g2_raw_bytes(p2)) == p2 and bn.g2_from_bytes(bn.g2_compressed_bytes(p2)) == p2
+    assert bn.g1_from_bytes(bn.g1_raw_bytes(None)) is None
+    assert len(bn.g1_compressed_bytes(G1_GEN)) == 32 and len(bn.g2_compressed_bytes(G2_GEN)) == 64
+
+
+def test_merkle_tree_reference_semantics():
+    """mirrors src/utils/merkletree/merkletree_test.go: empty root, proofs verify, capacity guards."""
+    nil = merkle.nil_account_hash()
+    t = merkle.FixedDepthMerkleTree(8, nil, 200)
+    assert t.root == t.nil[8]
+    leaves = {k: ps.poseidon_bytes([bytes([k + 1]), b"\x09"]) for k in (0, 1, 2, 5, 77, 199)}
+    for k, v in leaves.items():
+        t.set(k, v)
+    t.build()
+    for k, v in leaves.items():
+        assert merkle.verify_proof(t.root, k, t.get_proof(k), v, 8)
+    assert merkle.verify_proof(t.root, 3, t.get_proof(3), nil, 8)         # unset key proves the nil leaf
+    assert not merkle.verify_proof(t.root, 0, t.get_proof(1), leaves[0], 8)
+    for bad in (lambda: merkle.FixedDepthMerkleTree(33, nil, 1), lambda: merkle.FixedDepthMerkleTree(0, nil, 1),
+                lambda: merkle.FixedDepthMerkleTree(3, nil, 9), lambda: t.set(200, nil)):
+        try:
+            bad(); assert False
+        except (ValueError, IndexError):
+            pass
+
+
+def test_padding_account_assets_rule():
+    """src/utils/utils_test.go:43-136: gaps are filled with the lowest unused indices first."""
+    flat = merkle.padding_account_assets([(3, 1, 2, 3, 4, 5), (7, 9, 9, 9, 9, 9)])
+    idx = flat[0::6]
+    assert len(flat) == 300 and idx == sorted(idx) and len(set(idx)) == 50 and idx[:5] == [0, 1, 2, 3, 4]
+    assert flat[3 * 6:3 * 6 + 6] == [3, 1, 2, 3, 4, 5]
+    full = [(i, 1, 0, 0, 0, 0) for i in range(50)]
+    assert merkle.padding_account_assets(full)[0::6] == list(range(50))
+    assert len(merkle.padding_account_assets([(i, 1, 0, 0, 0, 0) for i in range(51)])) == 3000
+    assert len(merkle.pack_triples(flat)) == 100
