@@ -1,0 +1,160 @@
+/* libzkpor_b200 -- C-ABI of the B200-native hot path of binance/zkmerkle-proof-of-solvency.
+ *
+ * This is the drop-in boundary: exactly the entry points a cgo shim needs to replace the
+ * bodies of the reference's hot calls, nothing else.  Each function cites the reference interface it replaces
+ * (paths relative to the reference repository).  The Go-side stubs are in INTEGRATION.md.
+ *
+ * Conventions
+ *   - status: every function returns int32_t, 0 = ZKPOR_OK; zkpor_last_error() gives the message of the last
+ *     failure on the calling thread.  Nothing throws or aborts across the boundary.
+ *   - field elements: 4 x u64 little-endian limbs, Montgomery form, R = 2^256 -- gnark-crypto's fr.Element /
+ *     fp.Element in memory, so Go passes unsafe.Pointer(&slice[0]) with zero copies.
+ *   - G1 affine = X||Y (64 B), G2 affine = X.A0||X.A1||Y.A0||Y.A1 (128 B), Montgomery limbs, infinity = all zero:
+ *     gnark-crypto's bn254.G1Affine / G2Affine in memory.
+ *   - hashes / Merkle nodes: 32-byte big-endian canonical (fr.Element.Bytes(); what merkletree.go stores).
+ *   - every pointer may be a host pointer or a CUDA device pointer of the context's device; the library detects
+ *     which (cudaPointerGetAttributes).  Host buffers are owned by the caller for the duration of the call only.
+ *   - a zkpor_ctx is bound to one GPU and is NOT re-entrant (one call in flight per ctx); different contexts may be
+ *     driven from different OS threads.
+ *   - there is no CPU fallback: without a CUDA device zkpor_ctx_create fails with ZKPOR_ERR_NO_DEVICE.
+ */
+#ifndef ZKPOR_B200_H
+#define ZKPOR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKPOR_OK 0
+#define ZKPOR_ERR_INVALID_ARG 1
+#define ZKPOR_ERR_NO_DEVICE 2
+#define ZKPOR_ERR_CUDA 3
+#define ZKPOR_ERR_OOM 4
+#define ZKPOR_ERR_STATE 5
+
+/* flags */
+#define ZKPOR_SCALARS_MONT 0u      /* scalars are Montgomery-form fr.Element (gnark memory layout) -- the default */
+#define ZKPOR_SCALARS_PLAIN 1u     /* scalars are canonical integers (4 x u64 LE)                               */
+
+typedef struct zkpor_ctx zkpor_ctx;
+typedef struct zkpor_pk zkpor_pk;
+typedef struct zkpor_tree zkpor_tree;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------ */
+const char *zkpor_version(void);
+const char *zkpor_last_error(void);
+int32_t zkpor_device_count(int32_t *out_count);
+int32_t zkpor_ctx_create(int32_t device_id, zkpor_ctx **out);
+int32_t zkpor_ctx_destroy(zkpor_ctx *ctx);
+int32_t zkpor_ctx_sync(zkpor_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int32_t zkpor_ctx_launch_count(zkpor_ctx *ctx, uint64_t *out);
+/* CUDA stream the context launches on, as a cudaStream_t cast to void* (for event timing by the caller) */
+int32_t zkpor_ctx_stream(zkpor_ctx *ctx, void **out_stream);
+/* device milliseconds spent in the kernels of the last call, by stage (CUDA events on the context's stream).
+ * stage names: zkpor_stage_name(i); returns the number of stages via *n. */
+int32_t zkpor_ctx_last_timings(zkpor_ctx *ctx, float *out_ms, int32_t cap, int32_t *n);
+const char *zkpor_stage_name(int32_t i);
+
+/* ---- multi-scalar multiplication -------------------------------------------------------------------------------
+ * Replaces gnark-crypto G1Jac.MultiExp / G2Jac.MultiExp (ecc/bn254/multiexp.go, out of tree) as called inside
+ * groth16.Prove -- src/prover/prover/prover.go:269.  out = sum_i scalars[i] * points[i], affine. */
+int32_t zkpor_msm_g1(zkpor_ctx *ctx, const void *points /* n x 64 B */, const void *scalars /* n x 32 B */, uint64_t n,
+                     uint32_t flags, void *out_affine64 /* host */);
+int32_t zkpor_msm_g2(zkpor_ctx *ctx, const void *points /* n x 128 B */, const void *scalars, uint64_t n, uint32_t flags,
+                     void *out_affine128 /* host */);
+/* Multi-GPU: the partial result of this rank's point chunk as an extended-Jacobian point (X,Y,ZZ,ZZZ; 128 B for G1,
+ * 256 B for G2) so that ranks can exchange partials (one NCCL all-gather) and finish with zkpor_g{1,2}_sum_partials. */
+int32_t zkpor_msm_g1_partial(zkpor_ctx *ctx, const void *points, const void *scalars, uint64_t n, uint32_t flags, void *out_xyzz128);
+int32_t zkpor_msm_g2_partial(zkpor_ctx *ctx, const void *points, const void *scalars, uint64_t n, uint32_t flags, void *out_xyzz256);
+int32_t zkpor_g1_sum_partials(const void *partials_xyzz /* host, k x 128 B */, uint32_t k, void *out_affine64);
+int32_t zkpor_g2_sum_partials(const void *partials_xyzz /* host, k x 256 B */, uint32_t k, void *out_affine128);
+
+/* ---- NTT -------------------------------------------------------------------------------------------------------
+ * Replaces gnark-crypto fft.Domain.FFT / FFTInverse (ecc/bn254/fr/fft, out of tree), same conventions:
+ * decimation 0 = DIF (natural in, bit-reversed out), 1 = DIT (bit-reversed in, natural out); coset = OnCoset()
+ * with shift 5; inverse includes the 1/n scaling.  In place over `data` (n = 2^log_n Montgomery elements). */
+int32_t zkpor_ntt(zkpor_ctx *ctx, void *data, uint32_t log_n, int32_t inverse, int32_t decimation, int32_t coset);
+/* gnark backend/groth16/bn254/prove.go computeH: a, b, c = R1CS evaluation vectors of length n_constraints,
+ * zero-padded to n = 2^log_n; out_h = n elements, bit-reversed coefficient order (pairs with pk.G1.Z as gnark
+ * stores it).  out_h may be host or device. */
+int32_t zkpor_compute_h(zkpor_ctx *ctx, const void *a, const void *b, const void *c, uint64_t n_constraints, uint32_t log_n,
+                        void *out_h);
+
+/* ---- Groth16 proving key resident in HBM -----------------------------------------------------------------------
+ * Replaces the in-memory groth16.ProvingKey filled by pk.UnsafeReadFrom (src/prover/prover/prover.go:342-346);
+ * the descriptor fields are gnark's bn254 ProvingKey fields (backend/groth16/bn254/setup.go, out of tree). */
+typedef struct {
+    uint32_t log_n;                  /* pk.Domain.Cardinality = 2^log_n                                           */
+    uint64_t n_wires;                /* len(InfinityA) = len(InfinityB) = number of wires                           */
+    uint64_t n_public;               /* r1cs.GetNbPublicVariables(), includes the ONE wire                          */
+    uint64_t n_a, n_b, n_k, n_z;     /* len(pk.G1.A), len(pk.G1.B) = len(pk.G2.B), len(pk.G1.K), len(pk.G1.Z)        */
+    const void *g1_a, *g1_b, *g1_k, *g1_z;     /* affine arrays                                                     */
+    const void *g2_b;
+    const void *g1_alpha, *g1_beta, *g1_delta; /* single points                                                     */
+    const void *g2_beta, *g2_delta;
+    const uint8_t *infinity_a, *infinity_b;    /* n_wires bytes each (Go []bool)                                     */
+    uint64_t n_committed;            /* len(CommitmentKeys[0].Basis); 0 = circuit without commitment                */
+    const void *ck_basis, *ck_basis_exp_sigma;
+    const uint64_t *private_committed;         /* n_committed wire indices (ascending)                              */
+    uint64_t commitment_index;       /* wire index of the commitment (challenge) wire                               */
+} zkpor_pk_desc;
+int32_t zkpor_pk_upload(zkpor_ctx *ctx, const zkpor_pk_desc *desc, zkpor_pk **out);
+int32_t zkpor_pk_free(zkpor_ctx *ctx, zkpor_pk *pk);
+
+/* Pedersen commitment of the BSB22 hint: commitment = MSM(pk.CommitmentKeys[0].Basis, values)
+ * (gnark-crypto fr/pedersen ProvingKey.Commit; called mid-solve by Prove's hint override). */
+int32_t zkpor_pk_commit(zkpor_ctx *ctx, zkpor_pk *pk, const void *committed_values, void *out_affine64);
+
+/* Replaces the body of groth16.Prove after the solver has run (src/prover/prover/prover.go:269):
+ *   wires   = solution.W            (n_wires Montgomery elements)
+ *   a, b, c = solution.A/B/C        (n_constraints each)
+ *   r, s    = the blinding scalars gnark draws with crypto/rand, canonical 32-byte big-endian
+ * out_proof = proof.WriteRawTo bytes: Ar 64 | Bs 128 | Krs 64 | u32be nbCommitments | Commitment 64 | Pok 64
+ * (388 bytes with one commitment, 324 with none). */
+int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, const void *a, const void *b, const void *c,
+                            uint64_t n_constraints, const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof,
+                            uint32_t *out_len);
+/* Multi-GPU variant: every MSM runs on this rank's chunk of the key (the pk uploaded on this ctx holds only that chunk;
+ * see zkpor_pk_desc and INTEGRATION.md); returns the 7 partial sums (Ar, Bs1, Krs-K, Krs-Z, Commit, Pok as G1 XYZZ
+ * 128 B each, then Bs as G2 XYZZ 256 B) for one all-gather.  zkpor_groth16_finish combines k ranks' partials. */
+#define ZKPOR_PROVE_PARTIAL_BYTES (6 * 128 + 256)
+int32_t zkpor_groth16_prove_partial(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires_a, const void *wires_b, const void *wires_k,
+                                    const void *committed, const void *h_chunk, uint64_t n_h, void *out_partials);
+int32_t zkpor_groth16_finish(const void *partials /* k x ZKPOR_PROVE_PARTIAL_BYTES */, uint32_t k, const void *g1_alpha,
+                             const void *g1_beta, const void *g1_delta, const void *g2_beta, const void *g2_delta,
+                             const uint8_t r_be[32], const uint8_t s_be[32], int32_t has_commitment, uint8_t *out_proof,
+                             uint32_t *out_len);
+
+/* ---- Poseidon / Merkle -----------------------------------------------------------------------------------------
+ * Replaces the bnb-chain gnark-crypto fr/poseidon hashers (poseidon.Poseidon / PoseidonBytes / NewPoseidon, call
+ * sites src/utils/account_tree.go:19,27, src/utils/utils.go:748, src/witness/main.go:181) as batch calls. */
+/* output lane of the permutation (see DESIGN.md "Poseidon parity"): default 1 (the in-tree fixture), 0 = iden3 */
+int32_t zkpor_poseidon_set_out_lane(zkpor_ctx *ctx, int32_t lane);
+/* count independent hashes of n_in big-endian 32-byte elements each -> count x 32 B (PoseidonBytes semantics) */
+int32_t zkpor_poseidon_hash_batch(zkpor_ctx *ctx, const void *in_be, uint32_t n_in, uint64_t count, void *out_be);
+/* utils.AccountInfoToHash for a batch of accounts of one asset tier (src/utils/utils.go:744-750,188-221):
+ * ids = n x 32 B BE, totals = n x 3 x 32 B BE (equity, debt, collateral), flat_assets = n x tier*6 u64 already laid
+ * out by PaddingAccountAssets (host logic).  out = n x 32 B leaf hashes. */
+int32_t zkpor_account_leaves(zkpor_ctx *ctx, const void *ids_be, const void *totals_be, const void *flat_assets, uint64_t n,
+                             uint32_t tier, void *out_be);
+
+/* merkletree.NewFixedDepthMerkleTree / Set / Build / Root / GetProof (src/utils/merkletree/merkletree.go:137-308).
+ * The tree lives in HBM; leaves are uploaded in ranges (Set), Build hashes all levels, proofs are gathered in
+ * batches. */
+int32_t zkpor_tree_create(zkpor_ctx *ctx, uint32_t depth, const uint8_t nil_leaf[32], uint64_t capacity, zkpor_tree **out);
+int32_t zkpor_tree_free(zkpor_ctx *ctx, zkpor_tree *t);
+int32_t zkpor_tree_set_range(zkpor_ctx *ctx, zkpor_tree *t, uint64_t first_key, uint64_t count, const void *leaves_be);
+int32_t zkpor_tree_set_keys(zkpor_ctx *ctx, zkpor_tree *t, const uint32_t *keys, uint64_t count, const void *leaves_be);
+int32_t zkpor_tree_build(zkpor_ctx *ctx, zkpor_tree *t);
+int32_t zkpor_tree_root(zkpor_ctx *ctx, zkpor_tree *t, uint8_t out_root[32]);
+int32_t zkpor_tree_get_leaves(zkpor_ctx *ctx, zkpor_tree *t, const uint32_t *keys, uint64_t count, void *out_be);
+int32_t zkpor_tree_get_proofs(zkpor_ctx *ctx, zkpor_tree *t, const uint32_t *keys, uint64_t count, void *out_be /* count x depth x 32 */);
+/* device pointer of level `level` (0 = leaves) and its length in nodes, for multi-GPU subtree exchange */
+int32_t zkpor_tree_level(zkpor_ctx *ctx, zkpor_tree *t, uint32_t level, void **out_dev_ptr, uint64_t *out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -118,8 +118,10 @@ def _dot(terms, w):
     return sum(cf * w[i] for cf, i in terms) % R
 
 
-def solve(cs: R1CS, pk, public_inputs, secret_inputs):
-    """r1cs.Solve restated for the synthetic system.  Returns (wires, a, b, c, commitment_pt, committed_vals)."""
+def solve(cs: R1CS, pk, public_inputs, secret_inputs, commit_fn=None):
+    """r1cs.Solve restated for the synthetic system.  Returns (wires, a, b, c, commitment_pt, committed_vals).
+    commit_fn(values) -> affine point overrides the Pedersen commitment MSM (the BSB22 hint override of Prove);
+    the default uses the Python group law on pk["ck_basis"]."""
     w = [None] * cs.nb_wires
     w[0] = 1
     for i, v in enumerate(public_inputs):
@@ -131,7 +133,7 @@ def solve(cs: R1CS, pk, public_inputs, secret_inputs):
     for k in range(cs.nb_constraints):
         if cs.commitment_index >= 0 and k == cs.commit_after:
             committed_vals = [w[i] for i in cs.private_committed]
-            commitment_pt = bn.msm_naive(pk["ck_basis"], committed_vals)
+            commitment_pt = commit_fn(committed_vals) if commit_fn else bn.msm_naive(pk["ck_basis"], committed_vals)
             w[cs.commitment_index] = commitment_challenge(commitment_pt)
         av, bv = _dot(cs.L[k], w), _dot(cs.Rr[k], w)
         (cf, out), = cs.O[k]
@@ -148,9 +150,9 @@ def toxic_from_seed(seed: int):
     return {nm: 1 + rng.field(R - 1) for nm in names}
 
 
-def setup(cs: R1CS, toxic: dict):
-    """groth16.Setup with explicit toxic waste.  Returns (pk, vk); pk also carries the *scalars* behind each
-    point array (suffix _s) so the C oracle / CUDA tests can rebuild the same points with a fixed-base pass."""
+def setup_scalars(cs: R1CS, toxic: dict):
+    """The scalar side of groth16.Setup: the discrete logs (w.r.t. the generators) of every key element.
+    Cheap in Python; the points are k*G for these k (setup() below, or a fixed-base pass of the C oracle)."""
     d = Domain(cs.nb_constraints)
     n = d.n
     al, be, ga, de, tau, sigma = (toxic[k] for k in ("alpha", "beta", "gamma", "delta", "tau", "sigma"))
@@ -182,21 +184,26 @@ def setup(cs: R1CS, toxic: dict):
     for _ in range(n):
         Z_nat.append(zdt); zdt = zdt * tau % R
     Z = [Z_nat[bitrev(i, d.logn)] for i in range(n)][:n - 1]  # gnark >= 0.9: bit-reversed, n-1 kept
-    inf_a = [x == 0 for x in A]
-    inf_b = [x == 0 for x in B]
-    A_s = [x for x in A if x]
-    B_s = [x for x in B if x]
+    return dict(domain=d, log_n=d.logn, A_s=[x for x in A if x], B_s=[x for x in B if x], K_s=pkK, Z_s=Z, vkK_s=vkK,
+                infinity_a=[x == 0 for x in A], infinity_b=[x == 0 for x in B], ck_basis_s=ckK,
+                ck_sigma_s=[x * sigma % R for x in ckK])
+
+
+def setup(cs: R1CS, toxic: dict):
+    """groth16.Setup with explicit toxic waste.  Returns (pk, vk); pk also carries the *scalars* behind each
+    point array (suffix _s) so the C oracle / CUDA tests can rebuild the same points with a fixed-base pass."""
+    sc = setup_scalars(cs, toxic)
+    al, be, ga, de, sigma = (toxic[k] for k in ("alpha", "beta", "gamma", "delta", "sigma"))
     g1 = lambda s: pt_mul(G1_GEN, s)
     g2 = lambda s: pt_mul(G2_GEN, s, FP2)
     ped_g = g2(toxic["ped_g2"])
-    pk = dict(domain=d, alpha1=g1(al), beta1=g1(be), delta1=g1(de), beta2=g2(be), delta2=g2(de),
-              A_s=A_s, B_s=B_s, K_s=pkK, Z_s=Z, infinity_a=inf_a, infinity_b=inf_b,
-              A=[g1(s) for s in A_s], B1=[g1(s) for s in B_s], B2=[g2(s) for s in B_s],
-              K=[g1(s) for s in pkK], Z=[g1(s) for s in Z],
-              ck_basis_s=ckK, ck_basis=[g1(s) for s in ckK],
-              ck_basis_exp_sigma=[g1(s * sigma % R) for s in ckK])
+    pk = dict(sc)
+    pk.update(alpha1=g1(al), beta1=g1(be), delta1=g1(de), beta2=g2(be), delta2=g2(de),
+              A=[g1(s) for s in sc["A_s"]], B1=[g1(s) for s in sc["B_s"]], B2=[g2(s) for s in sc["B_s"]],
+              K=[g1(s) for s in sc["K_s"]], Z=[g1(s) for s in sc["Z_s"]],
+              ck_basis=[g1(s) for s in sc["ck_basis_s"]], ck_basis_exp_sigma=[g1(s) for s in sc["ck_sigma_s"]])
     vk = dict(alpha1=pk["alpha1"], beta1=pk["beta1"], delta1=pk["delta1"], beta2=pk["beta2"], delta2=pk["delta2"],
-              gamma2=g2(ga), K=[g1(s) for s in vkK], K_s=vkK,
+              gamma2=g2(ga), K=[g1(s) for s in sc["vkK_s"]], K_s=sc["vkK_s"],
               ped_g=ped_g, ped_g_root_sigma_neg=pt_mul(ped_g, (-pow(sigma, -1, R)) % R, FP2),
               public_and_commitment_committed=[[]] if cs.commitment_index >= 0 else [])
     return pk, vk

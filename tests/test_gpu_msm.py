@@ -1,0 +1,106 @@
+"""GPU parity: zkpor_msm_g1 / zkpor_msm_g2 through the C-ABI against the oracle (bit-exact affine output).
+Replaces gnark-crypto MultiExp inside groth16.Prove (src/prover/prover/prover.go:269)."""
+import numpy as np
+import pytest
+
+import bn254 as bn
+import orc
+import zkpor_b200 as zk
+from bn254 import FP2, G1_GEN, G2_GEN, R, SplitMix64
+from helpers import H, g1_points, g2_points, golden, rand_scalars, rand_scalars_np
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zk.Context(0)
+    yield c
+    c.close()
+
+
+def test_golden_msm_vectors(ctx):
+    m = golden()["msm"]
+    pk = orc.ints_to_limbs(H(m["point_scalars"]))
+    sc = orc.fr_mont(H(m["scalars"]))
+    assert orc.fp_unmont(ctx.msm_g1(orc.g1_fixed_base(pk), sc, len(sc))) == H(m["g1"])
+    assert orc.fp_unmont(ctx.msm_g2(orc.g2_fixed_base(pk), sc, len(sc))) == H(m["g2"])
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 257, 4096, 20000])
+@pytest.mark.parametrize("kind", ["uniform", "witness"])
+def test_g1_vs_oracle(ctx, n, kind):
+    pts = g1_points(n, 100 + n)
+    sc = orc.fr_mont(rand_scalars(n, 200 + n, kind))
+    assert np.array_equal(ctx.msm_g1(pts, sc, n), orc.g1_msm(pts, sc))
+
+
+@pytest.mark.parametrize("n", [1, 3, 500, 6000])
+@pytest.mark.parametrize("kind", ["uniform", "witness"])
+def test_g2_vs_oracle(ctx, n, kind):
+    pts = g2_points(n, 300 + n)
+    sc = orc.fr_mont(rand_scalars(n, 400 + n, kind))
+    assert np.array_equal(ctx.msm_g2(pts, sc, n), orc.g2_msm(pts, sc))
+
+
+def test_edge_cases(ctx):
+    n = 64
+    pts = g1_points(n, 7)
+    # all-zero scalars -> infinity; empty input -> infinity
+    assert not ctx.msm_g1(pts, orc.fr_mont([0] * n), n).any()
+    assert not ctx.msm_g1(pts, orc.fr_mont([0] * n), 0).any()
+    # repeated points in one bucket (doubling inside the accumulator), P and -P (passes through infinity), infinity inputs
+    pts[1] = pts[0]; pts[2] = pts[0]
+    negp = orc.g1_unpack(pts[3:4])[0]; pts[4] = orc.g1_pack([bn.pt_neg(negp)])[0]
+    pts[5] = 0
+    ss = [5, 5, 5, 9, 9, 1234] + rand_scalars(n - 6, 8)
+    ss[10] = R - 1; ss[11] = 1; ss[12] = (1 << 253) + 12345; ss[13] = (1 << 16); ss[14] = (1 << 15)
+    sc = orc.fr_mont(ss)
+    assert np.array_equal(ctx.msm_g1(pts, sc, n), orc.g1_msm(pts, sc))
+    # canonical (non-Montgomery) scalars
+    assert np.array_equal(ctx.msm_g1(pts, orc.ints_to_limbs(ss), n, zk.ZKPOR_SCALARS_PLAIN), orc.g1_msm(pts, sc))
+    # same scalar everywhere: one bucket per window gets every point
+    sc2 = orc.fr_mont([0xDEADBEEFCAFEF00D] * n)
+    assert np.array_equal(ctx.msm_g1(pts, sc2, n), orc.g1_msm(pts, sc2))
+
+
+def test_device_pointer_inputs(ctx):
+    import torch
+    n = 5000
+    pts = g1_points(n, 21); sc = orc.fr_mont(rand_scalars(n, 22))
+    tp = torch.from_numpy(pts.view(np.int64)).cuda(); ts = torch.from_numpy(sc.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    assert np.array_equal(ctx.msm_g1(tp, ts, n), orc.g1_msm(pts, sc))
+    t = ctx.last_timings()
+    assert t["h2d"] < 5.0 and t["accumulate"] > 0
+
+
+def test_partials_combine_like_multi_gpu(ctx):
+    """point-chunk sharding: sum of per-chunk partial results == whole MSM (what 8 ranks + one all-gather do)."""
+    n = 9000
+    pts = g1_points(n, 31); sc = orc.fr_mont(rand_scalars(n, 32))
+    cuts = [0, 1000, 1001, 5000, n]
+    parts = np.stack([ctx.msm_g1_partial(pts[a:b].copy(), sc[a:b].copy(), b - a) for a, b in zip(cuts, cuts[1:])])
+    assert np.array_equal(zk.g1_sum_partials(parts), orc.g1_msm(pts, sc))
+    p2 = g2_points(700, 33); s2 = orc.fr_mont(rand_scalars(700, 34))
+    parts2 = np.stack([ctx.msm_g2_partial(p2[a:b].copy(), s2[a:b].copy(), b - a) for a, b in ((0, 300), (300, 700))])
+    assert np.array_equal(zk.g2_sum_partials(parts2), orc.g2_msm(p2, s2))
+
+
+def test_g1_2pow20_vs_oracle_and_linearity(ctx):
+    """BASELINE config 2 smallest size, bit-exact against the CPU oracle; then the size-independent property
+    MSM(s) + MSM(t) = MSM(s + t) with resident points."""
+    import torch
+    n = 1 << 20
+    rng = SplitMix64(99)
+    base = orc.g1_fixed_base(orc.ints_to_limbs([1 + rng.field(R - 1) for _ in range(4096)]))
+    pts = np.ascontiguousarray(np.tile(base, (n // 4096, 1)))          # 2^20 points (repeats are legal inputs)
+    s = rand_scalars_np(n, 1); t = rand_scalars_np(n, 2)
+    got = ctx.msm_g1(pts, s, n)
+    assert np.array_equal(got, orc.g1_msm(pts, s))
+    dp = torch.from_numpy(pts.view(np.int64)).cuda()
+    # s + t mod r with Python ints in object arrays
+    S = np.array(orc.limbs_to_ints(s), dtype=object); T = np.array(orc.limbs_to_ints(t), dtype=object)
+    st = orc.ints_to_limbs(list((S + T) % R))
+    a = orc.g1_unpack(got)[0]; b = orc.g1_unpack(ctx.msm_g1(dp, t, n))[0]; c = orc.g1_unpack(ctx.msm_g1(dp, st, n))[0]
+    assert bn.pt_add(a, b) == c

@@ -1,0 +1,165 @@
+"""GPU parity: batched Poseidon, account leaves, FixedDepthMerkleTree through the C-ABI against the oracle and the
+reference's own fixture (src/verifier/config/user_config.json -> tests/golden/user_config_proof.json)."""
+import base64
+import json
+import os
+
+import numpy as np
+import pytest
+
+import merkle
+import orc
+import poseidon as ps
+import zkpor_b200 as zk
+from bn254 import R, SplitMix64
+from helpers import GOLDEN, H, golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zk.Context(0)
+    yield c
+    c.close()
+
+
+def test_reference_fixture_chain_on_gpu(ctx):
+    fx = json.load(open(os.path.join(GOLDEN, "user_config_proof.json")))
+    pr = [base64.b64decode(x) for x in fx["Proof"]]
+    ctx.set_poseidon_out_lane(1)
+    for i in range(15, 27):
+        assert ctx.poseidon_bytes(pr[i], pr[i]) == pr[i + 1]
+
+
+def test_published_vectors_lane0(ctx):
+    ctx.set_poseidon_out_lane(0)
+    assert ctx.poseidon_bytes(b"\x01", b"\x02").hex() == "115cc0f5e7d690413df64c6b9662e9cf2a3617f2743245519e19607a4417189a"
+    assert ctx.poseidon_bytes(b"\x01", b"\x02", b"\x03", b"\x04").hex() == "299c867db6c1fdd79dcefa40e4510b9837e60ebb1ce0663dbaa525df65250465"
+    assert int.from_bytes(ctx.poseidon_bytes(b"\x01"), "big") == 18586133768512220936620570745912940619677854269274689475585506675881198879027
+    ctx.set_poseidon_out_lane(1)
+
+
+def test_golden_poseidon_all_widths(ctx):
+    for lane in (0, 1):
+        ctx.set_poseidon_out_lane(lane)
+        for case in golden()["poseidon"]:
+            ins = H(case["in"])
+            got = ctx.poseidon_hash_batch(orc.be32_array(ins), len(ins), 1).tobytes()
+            assert got.hex() == "%064x" % int(case[f"lane{lane}"], 16)
+    ctx.set_poseidon_out_lane(1)
+
+
+@pytest.mark.parametrize("n_in", [1, 2, 5, 11, 12, 13, 25, 100])
+def test_hash_batch_vs_oracle(ctx, n_in):
+    rng = SplitMix64(n_in)
+    count = 37
+    vals = [rng.field(R) for _ in range(count * n_in)]
+    got = ctx.poseidon_hash_batch(orc.be32_array(vals), n_in, count)
+    for i in range(count):
+        want = orc.fr_unmont(orc.poseidon_hash(orc.fr_mont(vals[i * n_in:(i + 1) * n_in])))[0]
+        assert got[i].tobytes() == want.to_bytes(32, "big")
+
+
+def test_hasher_wrapper(ctx):
+    h = zk.PoseidonHasher(ctx)
+    h.write(b"\x00"); h.write(b"")
+    assert h.sum(b"ab") == b"ab" + ps.poseidon_bytes([b"\x00", b""])
+    assert h.data == []
+    with pytest.raises(ValueError):
+        h.write(R.to_bytes(32, "big"))
+
+
+def test_golden_account_leaves(ctx):
+    for lane in (0, 1):
+        ctx.set_poseidon_out_lane(lane)
+        for lv in golden()["leaves"]:
+            flat = zk.padding_account_assets([tuple(a) for a in lv["assets"]])
+            assert flat.tolist() == lv["flat"]
+            ids = np.frombuffer(bytes.fromhex(lv["id"]), dtype=np.uint8).copy()
+            tot = orc.be32_array([lv["equity"], lv["debt"], lv["collateral"]]).reshape(-1)
+            got = ctx.account_leaves(ids, tot, flat, 1, lv["tier"])
+            assert got.tobytes().hex() == lv[f"leaf_lane{lane}"]
+    ctx.set_poseidon_out_lane(1)
+
+
+@pytest.mark.parametrize("tier,n", [(50, 3001), (500, 203)])
+def test_account_leaves_batch_vs_oracle(ctx, tier, n):
+    rng = np.random.RandomState(tier)
+    flat = rng.randint(0, 1 << 62, size=(n, tier * 6), dtype=np.int64).astype(np.uint64)
+    ids = orc.be32_array([SplitMix64(i).field(R) for i in range(n)])
+    tot = orc.be32_array([int(x) for x in rng.randint(0, 1 << 62, size=n * 3)]).reshape(n, 96)
+    tot[5] = 0
+    got = ctx.account_leaves(ids, tot, flat, n, tier)
+    assert np.array_equal(got, orc.account_leaves(ids, tot, flat, tier))
+
+
+def test_golden_merkle(ctx):
+    for tv in golden()["merkle"]:
+        ctx.set_poseidon_out_lane(tv["lane"])
+        nil = bytes.fromhex(golden()["nil_account_hash"][f"lane{tv['lane']}"])
+        t = zk.FixedDepthMerkleTree(ctx, tv["depth"], nil, tv["capacity"])
+        assert t.root() == merkle.FixedDepthMerkleTree(tv["depth"], nil, tv["capacity"], tv["lane"]).root   # empty root = nilHashes[depth]
+        for k, v in tv["leaves"].items():
+            t.set(int(k), bytes.fromhex(v))
+        t.build()
+        assert t.root().hex() == tv["root"]
+        assert [x.hex() for x in t.get_proof(9)] == tv["proof_9"]
+        assert [x.hex() for x in t.get_proof(20)] == tv["proof_20"]
+        leaf9 = bytes.fromhex(tv["leaves"]["9"])
+        assert t.get(9) == leaf9 and t.get(20) == nil
+        assert zk.verify_proof(ctx, t.root(), 9, t.get_proof(9), leaf9, tv["depth"])
+        assert not zk.verify_proof(ctx, t.root(), 8, t.get_proof(9), leaf9, tv["depth"])
+        t.close()
+    ctx.set_poseidon_out_lane(1)
+
+
+@pytest.mark.parametrize("capacity,nset,depth", [(1, 1, 28), (2, 2, 5), (1000, 1000, 28), (100003, 77777, 28), (4096, 4096, 12)])
+def test_merkle_build_vs_oracle(ctx, capacity, nset, depth):
+    rng = np.random.RandomState(capacity)
+    leaves = rng.randint(0, 256, size=(capacity, 32)).astype(np.uint8); leaves[:, 0] &= 0x0F
+    nil = merkle.nil_account_hash(1)
+    t = zk.FixedDepthMerkleTree(ctx, depth, nil, capacity)
+    t.set_range(0, leaves[:nset].copy(), nset)
+    t.build()
+    dirty = np.zeros((capacity + 63) // 64, dtype=np.uint64)
+    for k in range(nset):
+        dirty[k >> 6] |= np.uint64(1 << (k & 63))
+    nodes, root = orc.merkle_build(leaves, capacity, depth, nil, dirty)
+    assert t.root() == root
+    keys = sorted(set([0, capacity - 1, nset - 1, min(nset, capacity - 1)] + [int(x) for x in rng.randint(0, capacity, size=50)]))
+    assert np.array_equal(t.get_proofs(keys), orc.merkle_proofs(leaves, nodes, capacity, depth, nil, keys, dirty))
+    t.close()
+
+
+def test_merkle_sparse_sets_and_rebuild(ctx):
+    """Set on arbitrary keys, Build, more Sets, Build again (merkletree_test.go multiple Set->Build cycles)."""
+    capacity, depth = 5000, 20
+    nil = merkle.nil_account_hash(1)
+    rng = np.random.RandomState(3)
+    leaves = np.zeros((capacity, 32), dtype=np.uint8)
+    dirty = np.zeros((capacity + 63) // 64, dtype=np.uint64)
+    t = zk.FixedDepthMerkleTree(ctx, depth, nil, capacity)
+    for rnd in range(2):
+        keys = np.unique(rng.randint(0, capacity, size=300)).astype(np.uint32)
+        vals = rng.randint(0, 256, size=(keys.size, 32)).astype(np.uint8); vals[:, 0] &= 0x0F
+        t.set_keys(keys, vals)
+        for k, v in zip(keys, vals):
+            leaves[k] = v; dirty[int(k) >> 6] |= np.uint64(1 << (int(k) & 63))
+        t.build()
+        _, root = orc.merkle_build(leaves, capacity, depth, nil, dirty)
+        assert t.root() == root
+
+
+def test_tree_argument_errors(ctx):
+    nil = bytes(32)
+    for args in ((33, 1), (0, 1), (3, 9)):
+        with pytest.raises(ValueError):
+            zk.FixedDepthMerkleTree(ctx, args[0], nil, args[1])
+    t = zk.FixedDepthMerkleTree(ctx, 4, nil, 10)
+    with pytest.raises(IndexError):
+        t.set(10, nil)
+    with pytest.raises(zk.ZkporError, match="out of range"):
+        t.set_range(8, np.zeros((3, 32), dtype=np.uint8), 3)
+    with pytest.raises(IndexError):
+        t.get_proof(16)

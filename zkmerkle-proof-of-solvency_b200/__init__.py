@@ -1,0 +1,432 @@
+"""zkpor_b200 -- thin ctypes binding of libzkpor_b200.so (CUDA sm_100a kernels behind the C-ABI in
+include/zkpor_b200.h) plus a host-side mirror of the reference interfaces this library replaces:
+
+  reference (Go)                                              here
+  ----------------------------------------------------------  -------------------------------------------
+  groth16.Prove(cs, pk, witness)      prover.go:269           ProvingKey(...).prove(wires, a, b, c, r, s)
+  pedersen ProvingKey.Commit          (inside Prove)          ProvingKey.commit(values)
+  G1Jac/G2Jac.MultiExp                (inside Prove)          Context.msm_g1 / msm_g2
+  fft.Domain.FFT/FFTInverse, computeH (inside Prove)          Context.ntt / compute_h
+  poseidon.PoseidonBytes / Poseidon   utils.go:748            Context.poseidon_bytes / poseidon_hash_batch
+  utils.AccountInfoToHash             utils.go:744-750        Context.account_leaves (+ padding_account_assets)
+  merkletree.FixedDepthMerkleTree     merkletree.go:27-355    FixedDepthMerkleTree(ctx, depth, nil, capacity)
+
+This module never computes on the CPU: there is no fallback.  If the shared library or a CUDA device is missing it
+raises -- loudly -- instead of returning anything.  It does not import anything under oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkpor_b200.so")
+
+R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+ZKPOR_SCALARS_MONT, ZKPOR_SCALARS_PLAIN = 0, 1
+PROVE_PARTIAL_BYTES = 6 * 128 + 256
+ASSET_TIERS = (50, 500)          # src/utils/constants.go:103-106
+ACCOUNT_TREE_DEPTH = 28          # src/utils/constants.go:18
+
+
+class ZkporError(RuntimeError):
+    pass
+
+
+def build_library(force: bool = False):
+    """Compile the CUDA extension for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-j8"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ZkporError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(the CUDA extension is mandatory; there is no CPU path)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.zkpor_last_error.restype = C.c_char_p
+        _lib.zkpor_version.restype = C.c_char_p
+        _lib.zkpor_stage_name.restype = C.c_char_p
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise ZkporError(f"zkpor error {rc}: {lib().zkpor_last_error().decode()}")
+
+
+def _ptr(x):
+    """numpy array -> host pointer; int -> raw (device) pointer; torch tensor -> data_ptr()"""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return C.c_void_p(x.ctypes.data)
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    raise TypeError(type(x))
+
+
+def device_count() -> int:
+    n = C.c_int32(0)
+    _check(lib().zkpor_device_count(C.byref(n)))
+    return n.value
+
+
+# ----------------------------------------------------------------------------------------------- host logic mirrors
+def assets_count_tier(n_assets: int) -> int:
+    """utils.GetAssetsCountOfUser (src/utils/utils.go:128-145)"""
+    for t in ASSET_TIERS:
+        if n_assets <= t:
+            return t
+    raise ValueError("the target counts is less than the length of assets")
+
+
+def padding_account_assets(assets) -> np.ndarray:
+    """utils.PaddingAccountAssets (src/utils/utils.go:147-186).  assets: rows (index, equity, debt, loan, margin,
+    portfolio_margin) with strictly increasing index -> flat uint64[tier*6]; gaps take the lowest unused indices."""
+    target = assets_count_tier(len(assets))
+    flat = np.zeros(target * 6, dtype=np.uint64)
+    padding = target - len(assets)
+    cur_pad, cur_idx, index = 0, 0, 0
+    for a in assets:
+        if cur_pad < padding:
+            for j in range(cur_idx, int(a[0])):
+                cur_pad += 1
+                flat[index * 6] = j
+                index += 1
+                if cur_pad >= padding:
+                    break
+        flat[index * 6:index * 6 + 6] = a
+        index += 1
+        cur_idx = int(a[0]) + 1
+    for i in range(index, target):
+        flat[i * 6] = cur_idx
+        cur_idx += 1
+    return flat
+
+
+def be32(v: int) -> bytes:
+    return int(v).to_bytes(32, "big")
+
+
+# ----------------------------------------------------------------------------------------------- context
+class Context:
+    """One GPU, one stream, NOT re-entrant (mirrors: one proof in flight per prover process, prover.go:141-247)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().zkpor_ctx_create(C.c_int32(device), C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().zkpor_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- bookkeeping
+    def sync(self):
+        _check(lib().zkpor_ctx_sync(self._h))
+
+    def launch_count(self) -> int:
+        n = C.c_uint64(0)
+        _check(lib().zkpor_ctx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        _check(lib().zkpor_ctx_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def last_timings(self) -> dict:
+        buf = (C.c_float * 16)()
+        n = C.c_int32(0)
+        _check(lib().zkpor_ctx_last_timings(self._h, buf, 16, C.byref(n)))
+        return {lib().zkpor_stage_name(i).decode(): float(buf[i]) for i in range(n.value)}
+
+    # --- MSM
+    def msm_g1(self, points, scalars, n: int, flags: int = ZKPOR_SCALARS_MONT) -> np.ndarray:
+        out = np.zeros(8, dtype=np.uint64)
+        _check(lib().zkpor_msm_g1(self._h, _ptr(points), _ptr(scalars), C.c_uint64(n), C.c_uint32(flags), _ptr(out)))
+        return out
+
+    def msm_g2(self, points, scalars, n: int, flags: int = ZKPOR_SCALARS_MONT) -> np.ndarray:
+        out = np.zeros(16, dtype=np.uint64)
+        _check(lib().zkpor_msm_g2(self._h, _ptr(points), _ptr(scalars), C.c_uint64(n), C.c_uint32(flags), _ptr(out)))
+        return out
+
+    def msm_g1_partial(self, points, scalars, n: int, flags: int = ZKPOR_SCALARS_MONT) -> np.ndarray:
+        out = np.zeros(16, dtype=np.uint64)
+        _check(lib().zkpor_msm_g1_partial(self._h, _ptr(points), _ptr(scalars), C.c_uint64(n), C.c_uint32(flags), _ptr(out)))
+        return out
+
+    def msm_g2_partial(self, points, scalars, n: int, flags: int = ZKPOR_SCALARS_MONT) -> np.ndarray:
+        out = np.zeros(32, dtype=np.uint64)
+        _check(lib().zkpor_msm_g2_partial(self._h, _ptr(points), _ptr(scalars), C.c_uint64(n), C.c_uint32(flags), _ptr(out)))
+        return out
+
+    # --- NTT
+    def ntt(self, data, log_n: int, inverse: bool, dit: bool, coset: bool):
+        """in place; data = numpy (host) or device pointer / tensor"""
+        _check(lib().zkpor_ntt(self._h, _ptr(data), C.c_uint32(log_n), C.c_int32(inverse), C.c_int32(dit), C.c_int32(coset)))
+        return data
+
+    def compute_h(self, a, b, c, n_constraints: int, log_n: int, out=None):
+        if out is None:
+            out = np.zeros((1 << log_n, 4), dtype=np.uint64)
+        _check(lib().zkpor_compute_h(self._h, _ptr(a), _ptr(b), _ptr(c), C.c_uint64(n_constraints), C.c_uint32(log_n), _ptr(out)))
+        return out
+
+    # --- Poseidon
+    def set_poseidon_out_lane(self, lane: int):
+        _check(lib().zkpor_poseidon_set_out_lane(self._h, C.c_int32(lane)))
+
+    def poseidon_hash_batch(self, in_be, n_in: int, count: int, out=None):
+        if out is None:
+            out = np.zeros((count, 32), dtype=np.uint8)
+        _check(lib().zkpor_poseidon_hash_batch(self._h, _ptr(in_be), C.c_uint32(n_in), C.c_uint64(count), _ptr(out)))
+        return out
+
+    def poseidon_bytes(self, *chunks: bytes) -> bytes:
+        """poseidon.PoseidonBytes(...[]byte): every chunk is one big-endian element (empty = 0), must be < r."""
+        vals = [int.from_bytes(c, "big") for c in chunks]
+        if any(v >= R_MOD for v in vals):
+            raise ValueError("not support bytes bigger than modulus")
+        buf = np.frombuffer(b"".join(be32(v) for v in vals), dtype=np.uint8).copy()
+        return self.poseidon_hash_batch(buf, len(vals), 1).tobytes()
+
+    def account_leaves(self, ids_be, totals_be, flat_assets, n: int, tier: int, out=None):
+        if out is None:
+            out = np.zeros((n, 32), dtype=np.uint8)
+        _check(lib().zkpor_account_leaves(self._h, _ptr(ids_be), _ptr(totals_be), _ptr(flat_assets), C.c_uint64(n), C.c_uint32(tier), _ptr(out)))
+        return out
+
+
+def g1_sum_partials(partials: np.ndarray) -> np.ndarray:
+    p = np.ascontiguousarray(partials, dtype=np.uint64).reshape(-1, 16)
+    out = np.zeros(8, dtype=np.uint64)
+    _check(lib().zkpor_g1_sum_partials(_ptr(p), C.c_uint32(p.shape[0]), _ptr(out)))
+    return out
+
+
+def g2_sum_partials(partials: np.ndarray) -> np.ndarray:
+    p = np.ascontiguousarray(partials, dtype=np.uint64).reshape(-1, 32)
+    out = np.zeros(16, dtype=np.uint64)
+    _check(lib().zkpor_g2_sum_partials(_ptr(p), C.c_uint32(p.shape[0]), _ptr(out)))
+    return out
+
+
+class PoseidonHasher:
+    """hash.Hash as returned by poseidon.NewPoseidon(): Write appends ONE element per call, Sum hashes and clears."""
+
+    def __init__(self, ctx: Context):
+        self.ctx, self.data = ctx, []
+
+    def reset(self):
+        self.data = []
+
+    def write(self, p: bytes) -> int:
+        if int.from_bytes(p, "big") >= R_MOD:
+            raise ValueError("not support bytes bigger than modulus")
+        self.data.append(bytes(p))
+        return len(p)
+
+    def sum(self, prefix: bytes = b"") -> bytes:
+        out = self.ctx.poseidon_bytes(*self.data)
+        self.data = []
+        return prefix + out
+
+
+# ----------------------------------------------------------------------------------------------- Merkle tree
+class FixedDepthMerkleTree:
+    """merkletree.FixedDepthMerkleTree with the tree resident in HBM (src/utils/merkletree/merkletree.go)."""
+
+    def __init__(self, ctx: Context, depth: int, nil_leaf: bytes, capacity: int):
+        if depth > 32:
+            raise ValueError("depth too large")
+        if depth <= 0:
+            raise ValueError("depth must be positive")
+        if capacity > (1 << depth):
+            raise ValueError("capacity exceeds maximum for given depth")
+        self.ctx, self.depth, self.capacity = ctx, depth, capacity
+        self._h = C.c_void_p()
+        nil = (C.c_uint8 * 32).from_buffer_copy(nil_leaf)
+        _check(lib().zkpor_tree_create(ctx._h, C.c_uint32(depth), nil, C.c_uint64(capacity), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().zkpor_tree_free(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set(self, key: int, value: bytes):
+        if key >= self.capacity:
+            raise IndexError(f"key {key} out of range for capacity {self.capacity}")
+        self.set_range(key, np.frombuffer(value, dtype=np.uint8).copy(), 1)
+
+    def set_range(self, first_key: int, leaves_be, count: int):
+        _check(lib().zkpor_tree_set_range(self.ctx._h, self._h, C.c_uint64(first_key), C.c_uint64(count), _ptr(leaves_be)))
+
+    def set_keys(self, keys, leaves_be):
+        k = np.ascontiguousarray(keys, dtype=np.uint32)
+        _check(lib().zkpor_tree_set_keys(self.ctx._h, self._h, _ptr(k), C.c_uint64(k.size), _ptr(leaves_be)))
+
+    def build(self):
+        _check(lib().zkpor_tree_build(self.ctx._h, self._h))
+
+    def root(self) -> bytes:
+        out = (C.c_uint8 * 32)()
+        _check(lib().zkpor_tree_root(self.ctx._h, self._h, out))
+        return bytes(out)
+
+    def get(self, key: int) -> bytes:
+        return self.get_leaves([key])[0].tobytes()
+
+    def get_leaves(self, keys) -> np.ndarray:
+        k = np.ascontiguousarray(keys, dtype=np.uint32)
+        out = np.zeros((k.size, 32), dtype=np.uint8)
+        _check(lib().zkpor_tree_get_leaves(self.ctx._h, self._h, _ptr(k), C.c_uint64(k.size), _ptr(out)))
+        return out
+
+    def get_proof(self, key: int):
+        if key >= (1 << self.depth):
+            raise IndexError(f"key {key} out of range for tree depth {self.depth}")
+        return [bytes(x) for x in self.get_proofs([key])[0]]
+
+    def get_proofs(self, keys) -> np.ndarray:
+        k = np.ascontiguousarray(keys, dtype=np.uint32)
+        out = np.zeros((k.size, self.depth, 32), dtype=np.uint8)
+        _check(lib().zkpor_tree_get_proofs(self.ctx._h, self._h, _ptr(k), C.c_uint64(k.size), _ptr(out)))
+        return out
+
+    def level(self, level: int):
+        p, n = C.c_void_p(), C.c_uint64(0)
+        _check(lib().zkpor_tree_level(self.ctx._h, self._h, C.c_uint32(level), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+
+def verify_proof(ctx: Context, root: bytes, key: int, proof, leaf: bytes, depth: int) -> bool:
+    """merkletree.VerifyProof (merkletree.go:334-355), hashing on the GPU one level at a time."""
+    if len(proof) != depth or key >= (1 << depth):
+        return False
+    node = leaf
+    for i in range(depth):
+        node = ctx.poseidon_bytes(node, proof[i]) if key & (1 << i) == 0 else ctx.poseidon_bytes(proof[i], node)
+    return node == root
+
+
+# ----------------------------------------------------------------------------------------------- Groth16
+class PkDesc(C.Structure):
+    _fields_ = [("log_n", C.c_uint32), ("n_wires", C.c_uint64), ("n_public", C.c_uint64),
+                ("n_a", C.c_uint64), ("n_b", C.c_uint64), ("n_k", C.c_uint64), ("n_z", C.c_uint64),
+                ("g1_a", C.c_void_p), ("g1_b", C.c_void_p), ("g1_k", C.c_void_p), ("g1_z", C.c_void_p), ("g2_b", C.c_void_p),
+                ("g1_alpha", C.c_void_p), ("g1_beta", C.c_void_p), ("g1_delta", C.c_void_p), ("g2_beta", C.c_void_p), ("g2_delta", C.c_void_p),
+                ("infinity_a", C.c_void_p), ("infinity_b", C.c_void_p),
+                ("n_committed", C.c_uint64), ("ck_basis", C.c_void_p), ("ck_basis_exp_sigma", C.c_void_p),
+                ("private_committed", C.c_void_p), ("commitment_index", C.c_uint64)]
+
+
+class ProvingKey:
+    """groth16.ProvingKey resident in HBM (what pk.UnsafeReadFrom fills at prover.go:342-346).  Arrays are numpy
+    uint64 in gnark memory layout, or device pointers / tensors for the point arrays."""
+
+    def __init__(self, ctx: Context, *, log_n, A, B1, K, Z, B2, alpha1, beta1, delta1, beta2, delta2, n_a, n_b, n_k, n_z,
+                 infinity_a=None, infinity_b=None, n_public=0, ck_basis=None, ck_basis_exp_sigma=None, private_committed=None,
+                 commitment_index=0):
+        self.ctx = ctx
+        d = PkDesc()
+        keep = []
+
+        def hp(x, dtype):
+            if x is None:
+                return None
+            if isinstance(x, np.ndarray):
+                x = np.ascontiguousarray(x, dtype=dtype)
+            keep.append(x)
+            return _ptr(x)
+
+        d.log_n = log_n
+        d.n_wires = 0 if infinity_a is None else len(infinity_a)
+        d.n_public = n_public
+        d.n_a, d.n_b, d.n_k, d.n_z = n_a, n_b, n_k, n_z
+        d.g1_a, d.g1_b, d.g1_k, d.g1_z, d.g2_b = (hp(x, np.uint64) for x in (A, B1, K, Z, B2))
+        d.g1_alpha, d.g1_beta, d.g1_delta, d.g2_beta, d.g2_delta = (hp(x, np.uint64) for x in (alpha1, beta1, delta1, beta2, delta2))
+        d.infinity_a = hp(None if infinity_a is None else np.asarray(infinity_a, dtype=np.uint8), np.uint8)
+        d.infinity_b = hp(None if infinity_b is None else np.asarray(infinity_b, dtype=np.uint8), np.uint8)
+        n_ck = 0
+        if ck_basis is not None:
+            n_ck = len(private_committed) if private_committed is not None else (ck_basis.size // 8)
+        d.n_committed = n_ck
+        d.ck_basis, d.ck_basis_exp_sigma = hp(ck_basis, np.uint64), hp(ck_basis_exp_sigma, np.uint64)
+        d.private_committed = hp(None if private_committed is None else np.asarray(private_committed, dtype=np.uint64), np.uint64)
+        d.commitment_index = commitment_index
+        self.points = dict(alpha1=np.array(alpha1, dtype=np.uint64), beta1=np.array(beta1, dtype=np.uint64), delta1=np.array(delta1, dtype=np.uint64),
+                           beta2=np.array(beta2, dtype=np.uint64), delta2=np.array(delta2, dtype=np.uint64))
+        self.has_commitment = ck_basis is not None
+        self.log_n, self.n_z = log_n, n_z
+        self._h = C.c_void_p()
+        _check(lib().zkpor_pk_upload(ctx._h, C.byref(d), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().zkpor_pk_free(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def commit(self, committed_values) -> np.ndarray:
+        out = np.zeros(8, dtype=np.uint64)
+        _check(lib().zkpor_pk_commit(self.ctx._h, self._h, _ptr(committed_values), _ptr(out)))
+        return out
+
+    def prove(self, wires, a, b, c, n_constraints: int, r: int, s: int) -> bytes:
+        """groth16.Prove after the solver: returns proof.WriteRawTo bytes."""
+        out = np.zeros(388, dtype=np.uint8)
+        n = C.c_uint32(0)
+        rb = (C.c_uint8 * 32).from_buffer_copy(be32(r % R_MOD))
+        sb = (C.c_uint8 * 32).from_buffer_copy(be32(s % R_MOD))
+        _check(lib().zkpor_groth16_prove(self.ctx._h, self._h, _ptr(wires), _ptr(a), _ptr(b), _ptr(c), C.c_uint64(n_constraints), rb, sb,
+                                         _ptr(out), C.byref(n)))
+        return out[:n.value].tobytes()
+
+    def prove_partial(self, wires_a, wires_b, wires_k, committed, h_chunk, n_h: int) -> np.ndarray:
+        out = np.zeros(PROVE_PARTIAL_BYTES, dtype=np.uint8)
+        _check(lib().zkpor_groth16_prove_partial(self.ctx._h, self._h, _ptr(wires_a), _ptr(wires_b), _ptr(wires_k), _ptr(committed),
+                                                 _ptr(h_chunk), C.c_uint64(n_h), _ptr(out)))
+        return out
+
+    def finish(self, partials: np.ndarray, r: int, s: int) -> bytes:
+        p = np.ascontiguousarray(partials, dtype=np.uint8).reshape(-1, PROVE_PARTIAL_BYTES)
+        out = np.zeros(388, dtype=np.uint8)
+        n = C.c_uint32(0)
+        rb = (C.c_uint8 * 32).from_buffer_copy(be32(r % R_MOD))
+        sb = (C.c_uint8 * 32).from_buffer_copy(be32(s % R_MOD))
+        pts = self.points
+        _check(lib().zkpor_groth16_finish(_ptr(p), C.c_uint32(p.shape[0]), _ptr(pts["alpha1"]), _ptr(pts["beta1"]), _ptr(pts["delta1"]),
+                                          _ptr(pts["beta2"]), _ptr(pts["delta2"]), rb, sb, C.c_int32(self.has_commitment), _ptr(out), C.byref(n)))
+        return out[:n.value].tobytes()

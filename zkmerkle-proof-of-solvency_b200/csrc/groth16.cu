@@ -1,0 +1,277 @@
+// Groth16 Prove on the GPU with the proving key resident in HBM.
+//
+// Replaces the body of gnark's groth16.Prove (backend/groth16/bn254/prove.go, out of tree) after the constraint
+// solver has run -- call site src/prover/prover/prover.go:269 -- and gnark-crypto's pedersen Commit/ProveKnowledge:
+//   commitment = MSM(Basis, committed)                 pok = MSM(BasisExpSigma, committed)
+//   h   = computeH(a, b, c)                            (bit-reversed, pairs with pk.G1.Z as gnark stores it)
+//   Ar  = MSM(A, wA) + alpha1 + r*delta1               Bs1 = MSM(B1, wB) + beta1 + s*delta1
+//   Bs  = MSM(B2, wB) + s*delta2 + beta2
+//   Krs = MSM(K, wK) + MSM(Z, h[:n-1]) + (-r*s)*delta1 + s*Ar + r*Bs1
+// wA / wB drop the wires whose A / B query is the point at infinity (pk.InfinityA/B); wK drops the public wires, the
+// committed wires and the commitment wire.  Output = proof.WriteRawTo bytes.
+#include "internal.h"
+
+using namespace ff;
+using namespace ec;
+
+struct zkpor_pk {
+    uint32_t log_n = 0;
+    uint64_t n_wires = 0, n_a = 0, n_b = 0, n_k = 0, n_z = 0, n_ck = 0;
+    G1Affine *A = nullptr, *B1 = nullptr, *K = nullptr, *Z = nullptr, *ck = nullptr, *ck_sigma = nullptr;
+    G2Affine *B2 = nullptr;
+    uint32_t *idx_a = nullptr, *idx_b = nullptr, *idx_k = nullptr, *idx_c = nullptr;   // gather indices into the wire vector
+    G1Affine alpha1, beta1, delta1;
+    G2Affine beta2, delta2;
+    bool has_commitment = false;
+    zk::DevBuf wires, sub;
+};
+
+namespace zk {
+
+__global__ void k_gather_fr(const Fr *__restrict__ src, const uint32_t *__restrict__ idx, uint64_t n, Fr *__restrict__ dst) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 *s = reinterpret_cast<const uint4 *>(src + idx[i]);
+    uint4 *d = reinterpret_cast<uint4 *>(dst + i);
+    d[0] = __ldg(s); d[1] = __ldg(s + 1);
+}
+
+static int32_t upload(void **dst, const void *src, size_t bytes) {
+    *dst = nullptr;
+    if (bytes == 0) return ZKPOR_OK;
+    ZK_CUDA(cudaMalloc(dst, bytes));
+    ZK_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyDefault));
+    return ZKPOR_OK;
+}
+
+struct ProofParts { G1XYZZ ar, bs1, krs_k, krs_z, commit, pok; G2XYZZ bs2; };
+
+// gnark prove.go tail: blinding, Krs assembly, Jacobian -> affine, WriteRawTo layout
+static void assemble_proof(const ProofParts &pp, const G1Affine &alpha1, const G1Affine &beta1, const G1Affine &delta1, const G2Affine &beta2,
+                           const G2Affine &delta2, const uint8_t r_be[32], const uint8_t s_be[32], bool has_commitment, uint8_t *out,
+                           uint32_t *out_len) {
+    Fr r_plain, s_plain;
+    fe_from_be32(&r_plain, r_be); fe_from_be32(&s_plain, s_be);
+    Fr kr = Fr::from_mont(Fr::neg(Fr::mul(Fr::to_mont(r_plain), Fr::to_mont(s_plain))));   // -(r*s), plain
+    G1XYZZ d1 = G1XYZZ::from_affine(delta1);
+    G1XYZZ ar = pp.ar; ar.add_affine(alpha1, false); ar.add(d1.mul_256(r_plain.l));
+    G1XYZZ bs1 = pp.bs1; bs1.add_affine(beta1, false); bs1.add(d1.mul_256(s_plain.l));
+    G2XYZZ bs2 = pp.bs2; bs2.add(G2XYZZ::from_affine(delta2).mul_256(s_plain.l)); bs2.add_affine(beta2, false);
+    G1XYZZ krs = pp.krs_k; krs.add(d1.mul_256(kr.l)); krs.add(pp.krs_z);
+    krs.add(ar.mul_256(s_plain.l)); krs.add(bs1.mul_256(r_plain.l));
+    g1_to_raw_bytes(out, ar.to_affine());
+    g2_to_raw_bytes(out + 64, bs2.to_affine());
+    g1_to_raw_bytes(out + 192, krs.to_affine());
+    out[256] = 0; out[257] = 0; out[258] = 0; out[259] = has_commitment ? 1 : 0;
+    uint32_t len = 260;
+    if (has_commitment) {
+        g1_to_raw_bytes(out + 260, pp.commit.to_affine()); len += 64;
+        g1_to_raw_bytes(out + len, pp.pok.to_affine()); len += 64;
+    } else {
+        // gnark writes CommitmentPok unconditionally: the zero point
+        g1_to_raw_bytes(out + len, G1Affine::inf()); len += 64;
+    }
+    *out_len = len;
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+extern "C" {
+
+int32_t zkpor_pk_free(zkpor_ctx *ctx, zkpor_pk *pk) {
+    (void)ctx;
+    if (!pk) return ZKPOR_OK;
+    void *ptrs[] = {pk->A, pk->B1, pk->K, pk->Z, pk->ck, pk->ck_sigma, pk->B2, pk->idx_a, pk->idx_b, pk->idx_k, pk->idx_c};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    pk->wires.release(); pk->sub.release();
+    delete pk;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_pk_upload(zkpor_ctx *ctx, const zkpor_pk_desc *d, zkpor_pk **out) {
+    ZK_REQUIRE(ctx && d && out, "pk_upload: null argument");
+    ZK_REQUIRE(d->log_n >= 1 && d->log_n <= 28, "pk_upload: log_n out of range");
+    ZK_REQUIRE(d->g1_alpha && d->g1_beta && d->g1_delta && d->g2_beta && d->g2_delta, "pk_upload: missing alpha/beta/delta");
+    ZK_REQUIRE(d->n_wires < (1ull << 32), "pk_upload: too many wires");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    zkpor_pk *pk = new zkpor_pk();
+    *out = nullptr;
+    pk->log_n = d->log_n; pk->n_wires = d->n_wires;
+    pk->n_a = d->n_a; pk->n_b = d->n_b; pk->n_k = d->n_k; pk->n_z = d->n_z; pk->n_ck = d->n_committed;
+    pk->has_commitment = d->n_committed > 0 || d->ck_basis != nullptr;
+    memcpy(&pk->alpha1, d->g1_alpha, 64); memcpy(&pk->beta1, d->g1_beta, 64); memcpy(&pk->delta1, d->g1_delta, 64);
+    memcpy(&pk->beta2, d->g2_beta, 128); memcpy(&pk->delta2, d->g2_delta, 128);
+    int32_t rc = ZKPOR_OK;
+    auto up = [&](void **dst, const void *src, size_t bytes) { if (rc == ZKPOR_OK) rc = upload(dst, src, bytes); };
+    up((void **)&pk->A, d->g1_a, d->n_a * 64); up((void **)&pk->B1, d->g1_b, d->n_b * 64); up((void **)&pk->K, d->g1_k, d->n_k * 64);
+    up((void **)&pk->Z, d->g1_z, d->n_z * 64); up((void **)&pk->B2, d->g2_b, d->n_b * 128);
+    up((void **)&pk->ck, d->ck_basis, d->n_committed * 64); up((void **)&pk->ck_sigma, d->ck_basis_exp_sigma, d->n_committed * 64);
+    if (rc == ZKPOR_OK && d->n_wires > 0) {
+        if (!d->infinity_a || !d->infinity_b) { set_error("pk_upload: infinity maps missing"); rc = ZKPOR_ERR_INVALID_ARG; }
+        else {
+            std::vector<uint32_t> ia, ib, ik, ic;
+            std::vector<uint8_t> drop(d->n_wires, 0);
+            for (uint64_t i = 0; i < d->n_committed; i++) {
+                if (d->private_committed[i] >= d->n_wires) { set_error("pk_upload: committed wire out of range"); rc = ZKPOR_ERR_INVALID_ARG; break; }
+                drop[d->private_committed[i]] = 1; ic.push_back((uint32_t)d->private_committed[i]);
+            }
+            if (rc == ZKPOR_OK && pk->has_commitment) {
+                if (d->commitment_index >= d->n_wires) { set_error("pk_upload: commitment wire out of range"); rc = ZKPOR_ERR_INVALID_ARG; }
+                else drop[d->commitment_index] = 1;
+            }
+            if (rc == ZKPOR_OK) {
+                for (uint64_t i = 0; i < d->n_wires; i++) {
+                    if (!d->infinity_a[i]) ia.push_back((uint32_t)i);
+                    if (!d->infinity_b[i]) ib.push_back((uint32_t)i);
+                    if (i >= d->n_public && !drop[i]) ik.push_back((uint32_t)i);
+                }
+                if (ia.size() != d->n_a || ib.size() != d->n_b || ik.size() != d->n_k) {
+                    set_error("pk_upload: key sizes inconsistent with infinity/commitment maps (A %zu/%llu, B %zu/%llu, K %zu/%llu)", ia.size(),
+                              (unsigned long long)d->n_a, ib.size(), (unsigned long long)d->n_b, ik.size(), (unsigned long long)d->n_k);
+                    rc = ZKPOR_ERR_INVALID_ARG;
+                }
+            }
+            up((void **)&pk->idx_a, ia.data(), ia.size() * 4); up((void **)&pk->idx_b, ib.data(), ib.size() * 4);
+            up((void **)&pk->idx_k, ik.data(), ik.size() * 4); up((void **)&pk->idx_c, ic.data(), ic.size() * 4);
+        }
+    }
+    if (rc == ZKPOR_OK && d->n_z != (1ull << d->log_n) - 1 && d->n_wires > 0) { set_error("pk_upload: len(Z) must be 2^log_n - 1"); rc = ZKPOR_ERR_INVALID_ARG; }
+    if (rc != ZKPOR_OK) { zkpor_pk_free(ctx, pk); return rc; }
+    *out = pk;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_pk_commit(zkpor_ctx *ctx, zkpor_pk *pk, const void *committed_values, void *out_affine64) {
+    ZK_REQUIRE(ctx && pk && committed_values && out_affine64, "pk_commit: null argument");
+    ZK_REQUIRE(pk->has_commitment, "pk_commit: key has no commitment");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    stages_reset(ctx);
+    const void *ds;
+    ZK_TRY(to_device(ctx, committed_values, pk->n_ck * 32, ctx->in_scalars, &ds));
+    G1XYZZ r; ZK_TRY(msm_g1_dev(ctx, pk->ck, ds, pk->n_ck, ZKPOR_SCALARS_MONT, &r));
+    G1Affine a = r.to_affine(); memcpy(out_affine64, &a, 64);
+    stages_collect(ctx);
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, const void *a, const void *b, const void *c,
+                            uint64_t n_constraints, const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
+    ZK_REQUIRE(ctx && pk && wires && a && b && c && r_be && s_be && out_proof && out_len, "prove: null argument");
+    ZK_REQUIRE(pk->n_wires > 0, "prove: key was uploaded without wire maps (sharded key?)");
+    const size_t n = (size_t)1 << pk->log_n;
+    ZK_REQUIRE(n_constraints > 0 && n_constraints <= n, "prove: n_constraints exceeds the domain");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    stages_reset(ctx);
+    // wires -> HBM
+    const void *dw;
+    stage_begin(ctx, ST_H2D);
+    ZK_TRY(to_device(ctx, wires, pk->n_wires * 32, pk->wires, &dw));
+    // a, b, c -> padded device vectors
+    const size_t bytes = n * sizeof(Fr), in_bytes = n_constraints * sizeof(Fr);
+    ZK_TRY(ctx->ntt_a.reserve(bytes)); ZK_TRY(ctx->ntt_b.reserve(bytes)); ZK_TRY(ctx->ntt_c.reserve(bytes));
+    const void *src[3] = {a, b, c};
+    Fr *dst[3] = {ctx->ntt_a.as<Fr>(), ctx->ntt_b.as<Fr>(), ctx->ntt_c.as<Fr>()};
+    for (int k = 0; k < 3; k++) {
+        ZK_CUDA(cudaMemcpyAsync(dst[k], src[k], in_bytes, cudaMemcpyDefault, ctx->stream));
+        if (bytes > in_bytes) ZK_CUDA(cudaMemsetAsync((uint8_t *)dst[k] + in_bytes, 0, bytes - in_bytes, ctx->stream));
+    }
+    stage_end(ctx, ST_H2D);
+    ZK_TRY(compute_h_dev(ctx, dst[0], dst[1], dst[2], pk->log_n));
+
+    uint64_t max_sub = pk->n_a; if (pk->n_b > max_sub) max_sub = pk->n_b; if (pk->n_k > max_sub) max_sub = pk->n_k; if (pk->n_ck > max_sub) max_sub = pk->n_ck;
+    ZK_TRY(pk->sub.reserve((max_sub ? max_sub : 1) * 32));
+    Fr *sub = pk->sub.as<Fr>();
+    ProofParts pp;
+    pp.commit = G1XYZZ::inf(); pp.pok = G1XYZZ::inf();
+    MsmSorted srt;
+    if (pk->has_commitment && pk->n_ck) {
+        ZK_LAUNCH(ctx, k_gather_fr, grid_for(pk->n_ck, 256), 256, 0, (const Fr *)dw, (const uint32_t *)pk->idx_c, pk->n_ck, sub);
+        ZK_TRY(msm_sort(ctx, sub, pk->n_ck, ZKPOR_SCALARS_MONT, &srt));
+        ZK_TRY(msm_accumulate_g1(ctx, pk->ck, srt, &pp.commit));
+        ZK_TRY(msm_accumulate_g1(ctx, pk->ck_sigma, srt, &pp.pok));
+    }
+    pp.ar = G1XYZZ::inf(); pp.bs1 = G1XYZZ::inf(); pp.bs2 = G2XYZZ::inf(); pp.krs_k = G1XYZZ::inf(); pp.krs_z = G1XYZZ::inf();
+    if (pk->n_a) {
+        ZK_LAUNCH(ctx, k_gather_fr, grid_for(pk->n_a, 256), 256, 0, (const Fr *)dw, (const uint32_t *)pk->idx_a, pk->n_a, sub);
+        ZK_TRY(msm_g1_dev(ctx, pk->A, sub, pk->n_a, ZKPOR_SCALARS_MONT, &pp.ar));
+    }
+    if (pk->n_b) {
+        ZK_LAUNCH(ctx, k_gather_fr, grid_for(pk->n_b, 256), 256, 0, (const Fr *)dw, (const uint32_t *)pk->idx_b, pk->n_b, sub);
+        ZK_TRY(msm_sort(ctx, sub, pk->n_b, ZKPOR_SCALARS_MONT, &srt));      // one sort, two accumulations (G1 and G2)
+        ZK_TRY(msm_accumulate_g1(ctx, pk->B1, srt, &pp.bs1));
+        ZK_TRY(msm_accumulate_g2(ctx, pk->B2, srt, &pp.bs2));
+    }
+    if (pk->n_k) {
+        ZK_LAUNCH(ctx, k_gather_fr, grid_for(pk->n_k, 256), 256, 0, (const Fr *)dw, (const uint32_t *)pk->idx_k, pk->n_k, sub);
+        ZK_TRY(msm_g1_dev(ctx, pk->K, sub, pk->n_k, ZKPOR_SCALARS_MONT, &pp.krs_k));
+    }
+    ZK_TRY(msm_g1_dev(ctx, pk->Z, dst[0], pk->n_z, ZKPOR_SCALARS_MONT, &pp.krs_z));
+    assemble_proof(pp, pk->alpha1, pk->beta1, pk->delta1, pk->beta2, pk->delta2, r_be, s_be, pk->has_commitment, out_proof, out_len);
+    stages_collect(ctx);
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_groth16_prove_partial(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires_a, const void *wires_b, const void *wires_k,
+                                    const void *committed, const void *h_chunk, uint64_t n_h, void *out_partials) {
+    ZK_REQUIRE(ctx && pk && out_partials, "prove_partial: null argument");
+    ZK_REQUIRE(n_h <= pk->n_z, "prove_partial: h chunk longer than the Z chunk");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    stages_reset(ctx);
+    ProofParts pp;
+    pp.ar = G1XYZZ::inf(); pp.bs1 = G1XYZZ::inf(); pp.bs2 = G2XYZZ::inf(); pp.krs_k = G1XYZZ::inf(); pp.krs_z = G1XYZZ::inf();
+    pp.commit = G1XYZZ::inf(); pp.pok = G1XYZZ::inf();
+    const void *ds; MsmSorted srt;
+    if (pk->n_ck && committed) {
+        ZK_TRY(to_device(ctx, committed, pk->n_ck * 32, ctx->in_scalars, &ds));
+        ZK_TRY(msm_sort(ctx, ds, pk->n_ck, ZKPOR_SCALARS_MONT, &srt));
+        ZK_TRY(msm_accumulate_g1(ctx, pk->ck, srt, &pp.commit));
+        ZK_TRY(msm_accumulate_g1(ctx, pk->ck_sigma, srt, &pp.pok));
+    }
+    if (pk->n_a && wires_a) {
+        ZK_TRY(to_device(ctx, wires_a, pk->n_a * 32, ctx->in_scalars, &ds));
+        ZK_TRY(msm_g1_dev(ctx, pk->A, ds, pk->n_a, ZKPOR_SCALARS_MONT, &pp.ar));
+    }
+    if (pk->n_b && wires_b) {
+        ZK_TRY(to_device(ctx, wires_b, pk->n_b * 32, ctx->in_scalars, &ds));
+        ZK_TRY(msm_sort(ctx, ds, pk->n_b, ZKPOR_SCALARS_MONT, &srt));
+        ZK_TRY(msm_accumulate_g1(ctx, pk->B1, srt, &pp.bs1));
+        ZK_TRY(msm_accumulate_g2(ctx, pk->B2, srt, &pp.bs2));
+    }
+    if (pk->n_k && wires_k) {
+        ZK_TRY(to_device(ctx, wires_k, pk->n_k * 32, ctx->in_scalars, &ds));
+        ZK_TRY(msm_g1_dev(ctx, pk->K, ds, pk->n_k, ZKPOR_SCALARS_MONT, &pp.krs_k));
+    }
+    if (n_h && h_chunk) {
+        ZK_TRY(to_device(ctx, h_chunk, n_h * 32, ctx->in_scalars, &ds));
+        ZK_TRY(msm_g1_dev(ctx, pk->Z, ds, n_h, ZKPOR_SCALARS_MONT, &pp.krs_z));
+    }
+    uint8_t *o = (uint8_t *)out_partials;
+    memcpy(o, &pp.ar, 128); memcpy(o + 128, &pp.bs1, 128); memcpy(o + 256, &pp.krs_k, 128); memcpy(o + 384, &pp.krs_z, 128);
+    memcpy(o + 512, &pp.commit, 128); memcpy(o + 640, &pp.pok, 128); memcpy(o + 768, &pp.bs2, 256);
+    stages_collect(ctx);
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_groth16_finish(const void *partials, uint32_t k, const void *g1_alpha, const void *g1_beta, const void *g1_delta,
+                             const void *g2_beta, const void *g2_delta, const uint8_t r_be[32], const uint8_t s_be[32],
+                             int32_t has_commitment, uint8_t *out_proof, uint32_t *out_len) {
+    ZK_REQUIRE(partials && g1_alpha && g1_beta && g1_delta && g2_beta && g2_delta && r_be && s_be && out_proof && out_len, "finish: null argument");
+    ProofParts pp;
+    pp.ar = G1XYZZ::inf(); pp.bs1 = G1XYZZ::inf(); pp.bs2 = G2XYZZ::inf(); pp.krs_k = G1XYZZ::inf(); pp.krs_z = G1XYZZ::inf();
+    pp.commit = G1XYZZ::inf(); pp.pok = G1XYZZ::inf();
+    for (uint32_t i = 0; i < k; i++) {
+        const uint8_t *p = (const uint8_t *)partials + (size_t)i * ZKPOR_PROVE_PARTIAL_BYTES;
+        G1XYZZ g; G2XYZZ g2;
+        memcpy(&g, p, 128); pp.ar.add(g); memcpy(&g, p + 128, 128); pp.bs1.add(g); memcpy(&g, p + 256, 128); pp.krs_k.add(g);
+        memcpy(&g, p + 384, 128); pp.krs_z.add(g); memcpy(&g, p + 512, 128); pp.commit.add(g); memcpy(&g, p + 640, 128); pp.pok.add(g);
+        memcpy(&g2, p + 768, 256); pp.bs2.add(g2);
+    }
+    G1Affine al, be, de; G2Affine be2, de2;
+    memcpy(&al, g1_alpha, 64); memcpy(&be, g1_beta, 64); memcpy(&de, g1_delta, 64); memcpy(&be2, g2_beta, 128); memcpy(&de2, g2_delta, 128);
+    assemble_proof(pp, al, be, de, be2, de2, r_be, s_be, has_commitment != 0, out_proof, out_len);
+    return ZKPOR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// Internal (non-exported) interfaces between the translation units of libzkpor_b200.
+#pragma once
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace zk {
+
+// Window plan of one Pippenger run: c-bit signed digits, nwin windows, nb = 2^(c-1) buckets per window.
+struct MsmPlan { uint32_t c, nwin, nb; };
+MsmPlan msm_plan(uint64_t n);
+
+// Result of the scalar-side half of an MSM (digit extraction + counting sort by bucket), living in ctx scratch:
+// for window w, the signed point references of bucket b are sort_idx[w*n + off[w*nb+b] .. +cnt[w*nb+b]).
+struct MsmSorted { MsmPlan plan; uint64_t n; const uint32_t *idx, *off, *cnt; };
+
+int32_t msm_sort(zkpor_ctx *ctx, const void *d_scalars, uint64_t n, uint32_t flags, MsmSorted *out);
+int32_t msm_accumulate_g1(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, ec::G1XYZZ *host_out);
+int32_t msm_accumulate_g2(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, ec::G2XYZZ *host_out);
+// full device MSM on device-resident inputs; result as XYZZ on the host
+int32_t msm_g1_dev(zkpor_ctx *ctx, const void *d_points, const void *d_scalars, uint64_t n, uint32_t flags, ec::G1XYZZ *host_out);
+int32_t msm_g2_dev(zkpor_ctx *ctx, const void *d_points, const void *d_scalars, uint64_t n, uint32_t flags, ec::G2XYZZ *host_out);
+
+// NTT (device-resident data)
+int32_t ntt_dev(zkpor_ctx *ctx, ff::Fr *d_data, uint32_t log_n, bool inverse, bool dit, bool coset);
+int32_t compute_h_dev(zkpor_ctx *ctx, ff::Fr *d_a, ff::Fr *d_b, ff::Fr *d_c, uint32_t log_n);   // result in d_a (bit-reversed)
+
+// host helpers
+void fe_from_be32(ff::Fr *out_plain, const uint8_t be[32]);    // canonical big-endian -> plain limbs (not Montgomery)
+void g1_to_raw_bytes(uint8_t out[64], const ec::G1Affine &p);   // gnark RawBytes
+void g2_to_raw_bytes(uint8_t out[128], const ec::G2Affine &p);
+
+}  // namespace zk

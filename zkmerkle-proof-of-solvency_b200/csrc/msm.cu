@@ -1,0 +1,287 @@
+// BN254 multi-scalar multiplication on sm_100a: signed-digit Pippenger with a counting sort by bucket.
+//
+// Replaces gnark-crypto G1Jac.MultiExp / G2Jac.MultiExp (ecc/bn254/multiexp.go, out of tree) called from
+// groth16.Prove -- src/prover/prover/prover.go:269.  Pipeline (all on ctx->stream, points/scalars resident in HBM):
+//   1. k_from_mont      scalars Montgomery -> canonical                              (streaming, 64 B/term)
+//   2. k_digits<HIST>   c-bit signed digits of every scalar, histogram per (window, bucket)   (32 B/term read)
+//   3. k_scan           exclusive scan of the histogram per window
+//   4. k_digits<SCATTER> signed point references scattered to their bucket segment   (32 B read + 4*nwin B write)
+//   5. k_accumulate     one thread per (window, bucket): XYZZ += affine point, gathered 64/128 B loads
+//   6. k_reduce_seg / k_sum_groups   sum_b b*B_b per window by segmented running sums
+//   7. host             Horner over the nwin window sums (nwin*c doublings) -- O(1) work, 2 KB copied back
+// The result of an MSM is a group element, so any bucket order gives bit-identical affine output.
+#include "internal.h"
+
+using namespace ff;
+using namespace ec;
+
+namespace zk {
+
+MsmPlan msm_plan(uint64_t n) {
+    // cost model in mixed-add units: every window adds n points and reduces nb buckets with 2 general adds (~1.4x)
+    double best = 1e300; uint32_t best_c = 4;
+    for (uint32_t c = 3; c <= 20; c++) {
+        uint32_t nwin = (255 + c - 1) / c;
+        double nb = (double)(1u << (c - 1));
+        double cost = nwin * ((double)n + 2.8 * nb + 2000.0);
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    MsmPlan p; p.c = best_c; p.nwin = (255 + best_c - 1) / best_c; p.nb = 1u << (best_c - 1);
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------ scalar side
+__global__ void k_from_mont(const Fr *__restrict__ in, Fr *__restrict__ out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = Fr::from_mont(in[i]);
+}
+
+__device__ __forceinline__ uint32_t window_bits(const uint32_t *s, uint32_t off, uint32_t c) {
+    uint32_t limb = off >> 5, sh = off & 31;
+    uint64_t v = s[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+}
+
+// MODE 0: histogram.  MODE 1: scatter (cursor[] starts as the exclusive scan and is advanced atomically).
+template <int MODE>
+__global__ void k_digits(const uint32_t *__restrict__ scalars /* plain, 8 x u32 each */, uint64_t n, MsmPlan plan,
+                         uint32_t *__restrict__ counter, uint32_t *__restrict__ sorted) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + 8 * i);
+    uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < plan.nwin; w++) {
+        uint32_t d = window_bits(s, w * plan.c, plan.c) + carry;
+        uint32_t neg = 0;
+        if (d > plan.nb) { d = (1u << plan.c) - d; neg = 1; carry = 1; } else carry = 0;
+        if (d) {
+            size_t slot = (size_t)w * plan.nb + (d - 1);
+            if (MODE == 0) atomicAdd(&counter[slot], 1u);
+            else { uint32_t pos = atomicAdd(&counter[slot], 1u); sorted[(size_t)w * n + pos] = ((uint32_t)i << 1) | neg; }
+        }
+    }
+}
+
+// one block per window: exclusive scan of cnt -> off, and cur = off
+__global__ void k_scan(const uint32_t *__restrict__ cnt, uint32_t *__restrict__ off, uint32_t *__restrict__ cur, uint32_t nb) {
+    __shared__ uint32_t part[1024];
+    const uint32_t w = blockIdx.x, t = threadIdx.x, T = blockDim.x;
+    const uint32_t per = (nb + T - 1) / T, lo = t * per, hi = min(lo + per, nb);
+    const uint32_t *c = cnt + (size_t)w * nb;
+    uint32_t sum = 0;
+    for (uint32_t k = lo; k < hi; k++) sum += c[k];
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < T; d <<= 1) {   // Hillis-Steele inclusive scan over the per-thread sums
+        uint32_t v = t >= d ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - sum;
+    for (uint32_t k = lo; k < hi; k++) { off[(size_t)w * nb + k] = run; cur[(size_t)w * nb + k] = run; run += c[k]; }
+}
+
+// ------------------------------------------------------------------------------------------------ point side
+template <class F> __device__ __forceinline__ Affine<F> load_affine(const Affine<F> *p) {
+    Affine<F> r;
+    const uint4 *src = reinterpret_cast<const uint4 *>(p);
+    uint4 *dst = reinterpret_cast<uint4 *>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(Affine<F>) / 16); k++) dst[k] = __ldg(src + k);
+    return r;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict__ points, const uint32_t *__restrict__ sorted,
+                                                    const uint32_t *__restrict__ off, const uint32_t *__restrict__ cnt,
+                                                    uint64_t n, MsmPlan plan, XYZZ<F> *__restrict__ buckets) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)plan.nwin * plan.nb) return;
+    uint32_t w = (uint32_t)(t / plan.nb);
+    const uint32_t *idx = sorted + (size_t)w * n + off[t];
+    uint32_t m = cnt[t];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = 0; k < m; k++) {
+        uint32_t e = __ldg(idx + k);
+        Affine<F> p = load_affine(points + (e >> 1));
+        acc.add_affine(p, e & 1);
+    }
+    buckets[t] = acc;
+}
+
+// thread (w, seg): sum_{j in seg} (j+1) * B[w][j]  via running sums, segment length L
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce_seg(const XYZZ<F> *__restrict__ buckets, MsmPlan plan, uint32_t L, uint32_t segs,
+                                                    XYZZ<F> *__restrict__ partials) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= plan.nwin * segs) return;
+    uint32_t w = t / segs, seg = t % segs;
+    uint32_t lo = seg * L, hi = min(lo + L, plan.nb);
+    const XYZZ<F> *B = buckets + (size_t)w * plan.nb;
+    XYZZ<F> run = XYZZ<F>::inf(), sum = XYZZ<F>::inf();
+    for (uint32_t j = hi; j-- > lo;) { run.add(B[j]); sum.add(run); }
+    // sum = sum_j (j - lo + 1) B_j ; add lo * run
+    if (lo) sum.add(run.mul_u32(lo));
+    partials[t] = sum;
+}
+
+// out[w*groups_out + g] = sum_{k < group} in[w*count_in + g*group + k]
+template <class F>
+__global__ void __launch_bounds__(128) k_sum_groups(const XYZZ<F> *__restrict__ in, uint32_t count_in, uint32_t group, uint32_t groups_out,
+                                                    uint32_t nwin, XYZZ<F> *__restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nwin * groups_out) return;
+    uint32_t w = t / groups_out, g = t % groups_out;
+    uint32_t lo = g * group, hi = min(lo + group, count_in);
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = lo; k < hi; k++) acc.add(in[(size_t)w * count_in + k]);
+    out[t] = acc;
+}
+
+int32_t msm_sort(zkpor_ctx *ctx, const void *d_scalars, uint64_t n, uint32_t flags, MsmSorted *out) {
+    ZK_REQUIRE(n > 0 && n < (1ull << 31), "msm: n must be in [1, 2^31)");
+    MsmPlan plan = msm_plan(n);
+    const size_t slots = (size_t)plan.nwin * plan.nb;
+    ZK_TRY(ctx->bucket_cnt.reserve(slots * 4));
+    ZK_TRY(ctx->bucket_off.reserve(slots * 4));
+    ZK_TRY(ctx->bucket_cur.reserve(slots * 4));
+    ZK_TRY(ctx->sort_idx.reserve((size_t)plan.nwin * n * 4));
+    stage_begin(ctx, ST_DIGITS);
+    const uint32_t *plain = (const uint32_t *)d_scalars;
+    if (!(flags & ZKPOR_SCALARS_PLAIN)) {
+        ZK_TRY(ctx->misc.reserve(n * 32));
+        ZK_LAUNCH(ctx, k_from_mont, grid_for(n, 256), 256, 0, (const Fr *)d_scalars, ctx->misc.as<Fr>(), n);
+        plain = ctx->misc.as<uint32_t>();
+    }
+    ZK_CUDA(cudaMemsetAsync(ctx->bucket_cnt.p, 0, slots * 4, ctx->stream));
+    ZK_LAUNCH(ctx, k_digits<0>, grid_for(n, 256), 256, 0, plain, n, plan, ctx->bucket_cnt.as<uint32_t>(), (uint32_t *)nullptr);
+    stage_end(ctx, ST_DIGITS);
+    stage_begin(ctx, ST_SORT);
+    ZK_LAUNCH(ctx, k_scan, plan.nwin, 1024, 0, ctx->bucket_cnt.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(),
+              ctx->bucket_cur.as<uint32_t>(), plan.nb);
+    ZK_LAUNCH(ctx, k_digits<1>, grid_for(n, 256), 256, 0, plain, n, plan, ctx->bucket_cur.as<uint32_t>(), ctx->sort_idx.as<uint32_t>());
+    stage_end(ctx, ST_SORT);
+    out->plan = plan; out->n = n;
+    out->idx = ctx->sort_idx.as<uint32_t>(); out->off = ctx->bucket_off.as<uint32_t>(); out->cnt = ctx->bucket_cnt.as<uint32_t>();
+    return ZKPOR_OK;
+}
+
+template <class F>
+static int32_t msm_accumulate(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, XYZZ<F> *host_out) {
+    const MsmPlan plan = s.plan;
+    const size_t slots = (size_t)plan.nwin * plan.nb;
+    ZK_TRY(ctx->buckets.reserve(slots * sizeof(XYZZ<F>)));
+    stage_begin(ctx, ST_ACCUM);
+    ZK_LAUNCH(ctx, (k_accumulate<F>), grid_for(slots, 128), 128, 0, (const Affine<F> *)d_points, s.idx, s.off, s.cnt, s.n, plan,
+              ctx->buckets.as<XYZZ<F>>());
+    stage_end(ctx, ST_ACCUM);
+    stage_begin(ctx, ST_REDUCE);
+    const uint32_t L = plan.nb >= 32 ? 32 : plan.nb;
+    uint32_t count = (plan.nb + L - 1) / L;
+    ZK_TRY(ctx->partials.reserve((size_t)plan.nwin * count * sizeof(XYZZ<F>) * 2));
+    XYZZ<F> *cur = ctx->partials.as<XYZZ<F>>(), *nxt = cur + (size_t)plan.nwin * count;
+    ZK_LAUNCH(ctx, (k_reduce_seg<F>), grid_for((size_t)plan.nwin * count, 128), 128, 0, ctx->buckets.as<XYZZ<F>>(), plan, L, count, cur);
+    while (count > 1) {
+        uint32_t groups = (count + 31) / 32;
+        ZK_LAUNCH(ctx, (k_sum_groups<F>), grid_for((size_t)plan.nwin * groups, 128), 128, 0, cur, count, 32u, groups, plan.nwin, nxt);
+        XYZZ<F> *t = cur; cur = nxt; nxt = t; count = groups;
+    }
+    stage_end(ctx, ST_REDUCE);
+    // window sums -> host, Horner
+    std::vector<XYZZ<F>> ws(plan.nwin);
+    stage_begin(ctx, ST_D2H);
+    ZK_CUDA(cudaMemcpyAsync(ws.data(), cur, plan.nwin * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, ctx->stream));
+    stage_end(ctx, ST_D2H);
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    XYZZ<F> acc = ws[plan.nwin - 1];
+    for (int w = (int)plan.nwin - 2; w >= 0; w--) {
+        for (uint32_t k = 0; k < plan.c; k++) acc = acc.dbl();
+        acc.add(ws[w]);
+    }
+    *host_out = acc;
+    return ZKPOR_OK;
+}
+
+int32_t msm_accumulate_g1(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, G1XYZZ *o) { return msm_accumulate<Fp>(ctx, d_points, s, o); }
+int32_t msm_accumulate_g2(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, G2XYZZ *o) { return msm_accumulate<Fp2>(ctx, d_points, s, o); }
+
+int32_t msm_g1_dev(zkpor_ctx *ctx, const void *d_points, const void *d_scalars, uint64_t n, uint32_t flags, G1XYZZ *o) {
+    if (n == 0) { *o = G1XYZZ::inf(); return ZKPOR_OK; }
+    MsmSorted s; ZK_TRY(msm_sort(ctx, d_scalars, n, flags, &s));
+    return msm_accumulate<Fp>(ctx, d_points, s, o);
+}
+int32_t msm_g2_dev(zkpor_ctx *ctx, const void *d_points, const void *d_scalars, uint64_t n, uint32_t flags, G2XYZZ *o) {
+    if (n == 0) { *o = G2XYZZ::inf(); return ZKPOR_OK; }
+    MsmSorted s; ZK_TRY(msm_sort(ctx, d_scalars, n, flags, &s));
+    return msm_accumulate<Fp2>(ctx, d_points, s, o);
+}
+
+}  // namespace zk
+
+// ------------------------------------------------------------------------------------------------ C-ABI
+using namespace zk;
+
+template <class F>
+static int32_t msm_entry(zkpor_ctx *ctx, const void *points, const void *scalars, uint64_t n, uint32_t flags, XYZZ<F> *out) {
+    ZK_REQUIRE(ctx != nullptr, "msm: null context");
+    ZK_REQUIRE(n == 0 || (points != nullptr && scalars != nullptr), "msm: null input");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    stages_reset(ctx);
+    if (n == 0) { *out = XYZZ<F>::inf(); return ZKPOR_OK; }
+    const void *dp, *ds;
+    stage_begin(ctx, ST_H2D);
+    ZK_TRY(to_device(ctx, points, n * sizeof(Affine<F>), ctx->in_points, &dp));
+    ZK_TRY(to_device(ctx, scalars, n * 32, ctx->in_scalars, &ds));
+    stage_end(ctx, ST_H2D);
+    MsmSorted s;
+    ZK_TRY(msm_sort(ctx, ds, n, flags, &s));
+    ZK_TRY(msm_accumulate<F>(ctx, dp, s, out));
+    stages_collect(ctx);
+    return ZKPOR_OK;
+}
+
+extern "C" {
+
+int32_t zkpor_msm_g1(zkpor_ctx *ctx, const void *points, const void *scalars, uint64_t n, uint32_t flags, void *out_affine64) {
+    ZK_REQUIRE(out_affine64 != nullptr, "msm: null output");
+    G1XYZZ r; ZK_TRY(msm_entry<Fp>(ctx, points, scalars, n, flags, &r));
+    G1Affine a = r.to_affine(); memcpy(out_affine64, &a, sizeof a);
+    return ZKPOR_OK;
+}
+int32_t zkpor_msm_g2(zkpor_ctx *ctx, const void *points, const void *scalars, uint64_t n, uint32_t flags, void *out_affine128) {
+    ZK_REQUIRE(out_affine128 != nullptr, "msm: null output");
+    G2XYZZ r; ZK_TRY(msm_entry<Fp2>(ctx, points, scalars, n, flags, &r));
+    G2Affine a = r.to_affine(); memcpy(out_affine128, &a, sizeof a);
+    return ZKPOR_OK;
+}
+int32_t zkpor_msm_g1_partial(zkpor_ctx *ctx, const void *points, const void *scalars, uint64_t n, uint32_t flags, void *out) {
+    ZK_REQUIRE(out != nullptr, "msm: null output");
+    G1XYZZ r; ZK_TRY(msm_entry<Fp>(ctx, points, scalars, n, flags, &r)); memcpy(out, &r, sizeof r);
+    return ZKPOR_OK;
+}
+int32_t zkpor_msm_g2_partial(zkpor_ctx *ctx, const void *points, const void *scalars, uint64_t n, uint32_t flags, void *out) {
+    ZK_REQUIRE(out != nullptr, "msm: null output");
+    G2XYZZ r; ZK_TRY(msm_entry<Fp2>(ctx, points, scalars, n, flags, &r)); memcpy(out, &r, sizeof r);
+    return ZKPOR_OK;
+}
+int32_t zkpor_g1_sum_partials(const void *partials, uint32_t k, void *out_affine64) {
+    ZK_REQUIRE(partials != nullptr && out_affine64 != nullptr, "sum_partials: null argument");
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint32_t i = 0; i < k; i++) { G1XYZZ p; memcpy(&p, (const uint8_t *)partials + (size_t)i * sizeof p, sizeof p); acc.add(p); }
+    G1Affine a = acc.to_affine(); memcpy(out_affine64, &a, sizeof a);
+    return ZKPOR_OK;
+}
+int32_t zkpor_g2_sum_partials(const void *partials, uint32_t k, void *out_affine128) {
+    ZK_REQUIRE(partials != nullptr && out_affine128 != nullptr, "sum_partials: null argument");
+    G2XYZZ acc = G2XYZZ::inf();
+    for (uint32_t i = 0; i < k; i++) { G2XYZZ p; memcpy(&p, (const uint8_t *)partials + (size_t)i * sizeof p, sizeof p); acc.add(p); }
+    G2Affine a = acc.to_affine(); memcpy(out_affine128, &a, sizeof a);
+    return ZKPOR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// Scalar-field NTT on sm_100a and the Groth16 quotient computation.
+//
+// Replaces gnark-crypto fft.Domain.FFT / FFTInverse (ecc/bn254/fr/fft, out of tree) and gnark's computeH
+// (backend/groth16/bn254/prove.go, out of tree), both reached from src/prover/prover/prover.go:269.  Conventions are
+// gnark's: DIF = natural in / bit-reversed out, DIT = bit-reversed in / natural out, coset shift 5, inverse scales by
+// 1/n.  Each pass keeps 2^R elements of one butterfly group in registers and runs R levels on them (R = 3: radix-8),
+// so a 2^26 transform is 9 read+write sweeps of the vector; twiddles come from one cached table w^j, j < n/2.
+#include <map>
+#include "internal.h"
+
+using namespace ff;
+
+namespace zk {
+
+static const uint32_t ROOT_2_28_PLAIN[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu, 0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u};
+
+struct NttDomain {
+    uint32_t log_n = 0;
+    Fr *tw_fwd = nullptr, *tw_inv = nullptr;          // w^j, w^-j for j < n/2
+    Fr *cf_lo = nullptr, *cf_hi = nullptr;            // coset 5^e, two-level: lo[e & LO_MASK] * hi[e >> LO_BITS]
+    Fr *cs_lo = nullptr, *cs_hi = nullptr;            // 5^e / n (inverse-then-coset fused scaling of computeH)
+    Fr *ci_lo = nullptr, *ci_hi = nullptr;            // 5^-e * den / n
+    Fr *ni_lo = nullptr, *ni_hi = nullptr;            // 5^-e / n (plain coset inverse)
+    Fr n_inv;                                         // 1/n
+};
+struct NttCache { std::map<uint32_t, NttDomain> doms; };
+
+static const uint32_t LO_BITS = 12;
+
+// out[k] = extra * base^k
+__global__ void k_pow_table(Fr *out, Fr base, Fr extra, uint32_t count) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    Fr acc = extra, b = base;
+    for (uint32_t e = k; e; e >>= 1) { if (e & 1) acc = Fr::mul(acc, b); b = Fr::sqr(b); }
+    out[k] = acc;
+}
+// out[j] = lo[j & mask] * hi[j >> LO_BITS]
+__global__ void k_table_product(Fr *out, const Fr *lo, const Fr *hi, size_t count) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    out[j] = Fr::mul(lo[j & ((1u << LO_BITS) - 1)], hi[j >> LO_BITS]);
+}
+
+__device__ __forceinline__ Fr ld_fr(const Fr *p) {
+    Fr r; const uint4 *s = reinterpret_cast<const uint4 *>(p); uint4 *d = reinterpret_cast<uint4 *>(&r);
+    d[0] = s[0]; d[1] = s[1]; return r;
+}
+__device__ __forceinline__ Fr ldg_fr(const Fr *p) {
+    Fr r; const uint4 *s = reinterpret_cast<const uint4 *>(p); uint4 *d = reinterpret_cast<uint4 *>(&r);
+    d[0] = __ldg(s); d[1] = __ldg(s + 1); return r;
+}
+__device__ __forceinline__ void st_fr(Fr *p, const Fr &v) {
+    uint4 *d = reinterpret_cast<uint4 *>(p); const uint4 *s = reinterpret_cast<const uint4 *>(&v);
+    d[0] = s[0]; d[1] = s[1];
+}
+
+// R levels of decimation-in-frequency starting at level `level` (level 0 has half-size n/2)
+template <int R>
+__global__ void __launch_bounds__(256) k_ntt_dif(Fr *__restrict__ data, const Fr *__restrict__ tw, uint32_t log_n, uint32_t level) {
+    const uint32_t log_h = log_n - 1 - level, log_q = log_h - (R - 1);
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ((size_t)1 << (log_n - R))) return;
+    size_t j = t & (((size_t)1 << log_q) - 1), blk = t >> log_q;
+    Fr *p = data + (blk << (log_h + 1)) + j;
+    Fr x[1 << R];
+#pragma unroll
+    for (int k = 0; k < (1 << R); k++) x[k] = ld_fr(p + ((size_t)k << log_q));
+#pragma unroll
+    for (int l = 0; l < R; l++) {
+        const int dist = 1 << (R - 1 - l);
+        const uint32_t sh = log_n - 1 - (log_h - l);
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) {
+            if (k & dist) continue;
+            size_t o = j + ((size_t)(k & (dist - 1)) << log_q);
+            Fr w = ldg_fr(tw + (o << sh));
+            Fr u = x[k], v = x[k + dist];
+            x[k] = Fr::add(u, v);
+            x[k + dist] = Fr::mul(Fr::sub(u, v), w);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < (1 << R); k++) st_fr(p + ((size_t)k << log_q), x[k]);
+}
+
+// R levels of decimation-in-time starting at level `level` (level 0 has half-size 1)
+template <int R>
+__global__ void __launch_bounds__(256) k_ntt_dit(Fr *__restrict__ data, const Fr *__restrict__ tw, uint32_t log_n, uint32_t level) {
+    const uint32_t log_q = level;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ((size_t)1 << (log_n - R))) return;
+    size_t j = t & (((size_t)1 << log_q) - 1), blk = t >> log_q;
+    Fr *p = data + (blk << (log_q + R)) + j;
+    Fr x[1 << R];
+#pragma unroll
+    for (int k = 0; k < (1 << R); k++) x[k] = ld_fr(p + ((size_t)k << log_q));
+#pragma unroll
+    for (int l = 0; l < R; l++) {
+        const int dist = 1 << l;
+        const uint32_t sh = log_n - 1 - (log_q + l);
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) {
+            if (k & dist) continue;
+            size_t o = j + ((size_t)(k & (dist - 1)) << log_q);
+            Fr w = ldg_fr(tw + (o << sh));
+            Fr u = x[k], v = Fr::mul(x[k + dist], w);
+            x[k] = Fr::add(u, v);
+            x[k + dist] = Fr::sub(u, v);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < (1 << R); k++) st_fr(p + ((size_t)k << log_q), x[k]);
+}
+
+// data[i] *= lo[e & mask] * hi[e >> LO_BITS], e = i or bitrev(i)
+__global__ void k_scale_pow(Fr *__restrict__ data, const Fr *__restrict__ lo, const Fr *__restrict__ hi, uint32_t log_n, int bitrev) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ((size_t)1 << log_n)) return;
+    uint32_t e = bitrev ? (__brev((uint32_t)i) >> (32 - log_n)) : (uint32_t)i;
+    Fr f = Fr::mul(ldg_fr(lo + (e & ((1u << LO_BITS) - 1))), ldg_fr(hi + (e >> LO_BITS)));
+    st_fr(data + i, Fr::mul(ld_fr(data + i), f));
+}
+__global__ void k_scale_const(Fr *__restrict__ data, Fr f, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_fr(data + i, Fr::mul(ld_fr(data + i), f));
+}
+// a = a*b - c
+__global__ void k_ab_minus_c(Fr *__restrict__ a, const Fr *__restrict__ b, const Fr *__restrict__ c, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_fr(a + i, Fr::sub(Fr::mul(ld_fr(a + i), ld_fr(b + i)), ld_fr(c + i)));
+}
+
+static Fr host_pow_u64(Fr base, uint64_t e) {
+    Fr acc = Fr::one();
+    for (; e; e >>= 1) { if (e & 1) acc = Fr::mul(acc, base); base = Fr::sqr(base); }
+    return acc;
+}
+
+static int32_t build_two_level(zkpor_ctx *ctx, Fr base, Fr extra, uint32_t log_count, Fr **lo, Fr **hi) {
+    const uint32_t lo_n = log_count < LO_BITS ? (1u << log_count) : (1u << LO_BITS);
+    const uint32_t hi_n = log_count < LO_BITS ? 1u : (1u << (log_count - LO_BITS));
+    ZK_CUDA(cudaMalloc((void **)lo, sizeof(Fr) * lo_n));
+    ZK_CUDA(cudaMalloc((void **)hi, sizeof(Fr) * hi_n));
+    ZK_LAUNCH(ctx, k_pow_table, grid_for(lo_n, 128), 128, 0, *lo, base, Fr::one(), lo_n);
+    ZK_LAUNCH(ctx, k_pow_table, grid_for(hi_n, 128), 128, 0, *hi, host_pow_u64(base, 1ull << LO_BITS), extra, hi_n);
+    return ZKPOR_OK;
+}
+
+static int32_t get_domain(zkpor_ctx *ctx, uint32_t log_n, NttDomain **out) {
+    if (!ctx->ntt_tables) ctx->ntt_tables = new NttCache();
+    NttCache *cache = (NttCache *)ctx->ntt_tables;
+    auto it = cache->doms.find(log_n);
+    if (it != cache->doms.end()) { *out = &it->second; return ZKPOR_OK; }
+    NttDomain d; d.log_n = log_n;
+    Fr root; memcpy(root.l, ROOT_2_28_PLAIN, 32); root = Fr::to_mont(root);
+    for (uint32_t i = log_n; i < 28; i++) root = Fr::sqr(root);
+    const Fr gen = root, gen_inv = Fr::inv(root);
+    const Fr five = Fr::from_u64(5), five_inv = Fr::inv(five);
+    d.n_inv = Fr::inv(Fr::from_u64(1ull << log_n));
+    Fr den = five; for (uint32_t i = 0; i < log_n; i++) den = Fr::sqr(den);     // 5^n
+    den = Fr::inv(Fr::sub(den, Fr::one()));
+    const size_t half = log_n ? ((size_t)1 << (log_n - 1)) : 1;
+    // twiddle tables via a temporary two-level table
+    for (int dir = 0; dir < 2; dir++) {
+        Fr *lo, *hi, *full;
+        ZK_TRY(build_two_level(ctx, dir ? gen_inv : gen, Fr::one(), log_n ? log_n - 1 : 0, &lo, &hi));
+        ZK_CUDA(cudaMalloc((void **)&full, sizeof(Fr) * half));
+        ZK_LAUNCH(ctx, k_table_product, grid_for(half, 256), 256, 0, full, lo, hi, half);
+        ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(lo); cudaFree(hi);
+        (dir ? d.tw_inv : d.tw_fwd) = full;
+    }
+    ZK_TRY(build_two_level(ctx, five, Fr::one(), log_n, &d.cf_lo, &d.cf_hi));
+    ZK_TRY(build_two_level(ctx, five, d.n_inv, log_n, &d.cs_lo, &d.cs_hi));
+    ZK_TRY(build_two_level(ctx, five_inv, Fr::mul(d.n_inv, den), log_n, &d.ci_lo, &d.ci_hi));
+    ZK_TRY(build_two_level(ctx, five_inv, d.n_inv, log_n, &d.ni_lo, &d.ni_hi));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cache->doms[log_n] = d;
+    *out = &cache->doms[log_n];
+    return ZKPOR_OK;
+}
+
+static int32_t run_dif(zkpor_ctx *ctx, Fr *d, const Fr *tw, uint32_t log_n) {
+    uint32_t level = 0;
+    while (level < log_n) {
+        uint32_t R = log_n - level >= 3 ? 3 : log_n - level;
+        size_t threads = (size_t)1 << (log_n - R);
+        if (R == 3) ZK_LAUNCH(ctx, k_ntt_dif<3>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
+        else if (R == 2) ZK_LAUNCH(ctx, k_ntt_dif<2>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
+        else ZK_LAUNCH(ctx, k_ntt_dif<1>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
+        level += R;
+    }
+    return ZKPOR_OK;
+}
+static int32_t run_dit(zkpor_ctx *ctx, Fr *d, const Fr *tw, uint32_t log_n) {
+    uint32_t level = 0;
+    while (level < log_n) {
+        uint32_t R = log_n - level >= 3 ? 3 : log_n - level;
+        size_t threads = (size_t)1 << (log_n - R);
+        if (R == 3) ZK_LAUNCH(ctx, k_ntt_dit<3>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
+        else if (R == 2) ZK_LAUNCH(ctx, k_ntt_dit<2>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
+        else ZK_LAUNCH(ctx, k_ntt_dit<1>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
+        level += R;
+    }
+    return ZKPOR_OK;
+}
+
+int32_t ntt_dev(zkpor_ctx *ctx, Fr *d, uint32_t log_n, bool inverse, bool dit, bool coset) {
+    ZK_REQUIRE(log_n <= 28, "ntt: log_n exceeds the 2-adicity of Fr (28)");
+    if (log_n == 0) return ZKPOR_OK;
+    NttDomain *dom; ZK_TRY(get_domain(ctx, log_n, &dom));
+    const size_t n = (size_t)1 << log_n;
+    if (!inverse) {
+        if (coset) ZK_LAUNCH(ctx, k_scale_pow, grid_for(n, 256), 256, 0, d, dom->cf_lo, dom->cf_hi, log_n, dit ? 1 : 0);
+        ZK_TRY(dit ? run_dit(ctx, d, dom->tw_fwd, log_n) : run_dif(ctx, d, dom->tw_fwd, log_n));
+    } else {
+        ZK_TRY(dit ? run_dit(ctx, d, dom->tw_inv, log_n) : run_dif(ctx, d, dom->tw_inv, log_n));
+        if (coset) ZK_LAUNCH(ctx, k_scale_pow, grid_for(n, 256), 256, 0, d, dom->ni_lo, dom->ni_hi, log_n, dit ? 0 : 1);
+        else ZK_LAUNCH(ctx, k_scale_const, grid_for(n, 256), 256, 0, d, dom->n_inv, n);
+    }
+    return ZKPOR_OK;
+}
+
+// a, b, c: device vectors of n = 2^log_n elements (zero padded).  Result h in a, bit-reversed coefficient order.
+//   x <- DIF_inv(x); x[pos] *= 5^bitrev(pos)/n; x <- DIT_fwd(x)        for x in a, b, c
+//   a <- a*b - c ; a <- DIF_inv(a) ; a[pos] *= 5^-bitrev(pos) * den/n
+int32_t compute_h_dev(zkpor_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n) {
+    ZK_REQUIRE(log_n >= 1 && log_n <= 28, "compute_h: log_n out of range");
+    NttDomain *dom; ZK_TRY(get_domain(ctx, log_n, &dom));
+    const size_t n = (size_t)1 << log_n;
+    stage_begin(ctx, ST_NTT);
+    Fr *v[3] = {a, b, c};
+    for (int k = 0; k < 3; k++) {
+        ZK_TRY(run_dif(ctx, v[k], dom->tw_inv, log_n));
+        ZK_LAUNCH(ctx, k_scale_pow, grid_for(n, 256), 256, 0, v[k], dom->cs_lo, dom->cs_hi, log_n, 1);
+        ZK_TRY(run_dit(ctx, v[k], dom->tw_fwd, log_n));
+    }
+    ZK_LAUNCH(ctx, k_ab_minus_c, grid_for(n, 256), 256, 0, a, (const Fr *)b, (const Fr *)c, n);
+    ZK_TRY(run_dif(ctx, a, dom->tw_inv, log_n));
+    ZK_LAUNCH(ctx, k_scale_pow, grid_for(n, 256), 256, 0, a, dom->ci_lo, dom->ci_hi, log_n, 1);
+    stage_end(ctx, ST_NTT);
+    return ZKPOR_OK;
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+extern "C" {
+
+void zk_free_ntt(zkpor_ctx *ctx) {
+    if (!ctx->ntt_tables) return;
+    NttCache *cache = (NttCache *)ctx->ntt_tables;
+    for (auto &kv : cache->doms) {
+        NttDomain &d = kv.second;
+        Fr *ptrs[] = {d.tw_fwd, d.tw_inv, d.cf_lo, d.cf_hi, d.cs_lo, d.cs_hi, d.ci_lo, d.ci_hi, d.ni_lo, d.ni_hi};
+        for (Fr *p : ptrs) if (p) cudaFree(p);
+    }
+    delete cache;
+    ctx->ntt_tables = nullptr;
+}
+
+int32_t zkpor_ntt(zkpor_ctx *ctx, void *data, uint32_t log_n, int32_t inverse, int32_t decimation, int32_t coset) {
+    ZK_REQUIRE(ctx != nullptr && data != nullptr, "ntt: null argument");
+    ZK_REQUIRE(log_n <= 28, "ntt: log_n exceeds the 2-adicity of Fr (28)");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    stages_reset(ctx);
+    const size_t bytes = sizeof(Fr) << log_n;
+    const bool on_dev = is_device_ptr(data);
+    Fr *d = (Fr *)data;
+    if (!on_dev) {
+        ZK_TRY(ctx->ntt_a.reserve(bytes));
+        d = ctx->ntt_a.as<Fr>();
+        stage_begin(ctx, ST_H2D);
+        ZK_CUDA(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        stage_end(ctx, ST_H2D);
+    }
+    stage_begin(ctx, ST_NTT);
+    ZK_TRY(ntt_dev(ctx, d, log_n, inverse != 0, decimation != 0, coset != 0));
+    stage_end(ctx, ST_NTT);
+    if (!on_dev) {
+        stage_begin(ctx, ST_D2H);
+        ZK_CUDA(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        stage_end(ctx, ST_D2H);
+    }
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    stages_collect(ctx);
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_compute_h(zkpor_ctx *ctx, const void *a, const void *b, const void *c, uint64_t m, uint32_t log_n, void *out_h) {
+    ZK_REQUIRE(ctx != nullptr && a && b && c && out_h, "compute_h: null argument");
+    ZK_REQUIRE(log_n >= 1 && log_n <= 28 && m <= (1ull << log_n) && m > 0, "compute_h: size out of range");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    stages_reset(ctx);
+    const size_t n = (size_t)1 << log_n, bytes = n * sizeof(Fr), in_bytes = m * sizeof(Fr);
+    ZK_TRY(ctx->ntt_a.reserve(bytes)); ZK_TRY(ctx->ntt_b.reserve(bytes)); ZK_TRY(ctx->ntt_c.reserve(bytes));
+    const void *src[3] = {a, b, c};
+    Fr *dst[3] = {ctx->ntt_a.as<Fr>(), ctx->ntt_b.as<Fr>(), ctx->ntt_c.as<Fr>()};
+    stage_begin(ctx, ST_H2D);
+    for (int k = 0; k < 3; k++) {
+        ZK_CUDA(cudaMemcpyAsync(dst[k], src[k], in_bytes, cudaMemcpyDefault, ctx->stream));
+        if (bytes > in_bytes) ZK_CUDA(cudaMemsetAsync((uint8_t *)dst[k] + in_bytes, 0, bytes - in_bytes, ctx->stream));
+    }
+    stage_end(ctx, ST_H2D);
+    ZK_TRY(compute_h_dev(ctx, dst[0], dst[1], dst[2], log_n));
+    stage_begin(ctx, ST_D2H);
+    ZK_CUDA(cudaMemcpyAsync(out_h, dst[0], bytes, cudaMemcpyDefault, ctx->stream));
+    stage_end(ctx, ST_D2H);
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    stages_collect(ctx);
+    return ZKPOR_OK;
+}
+
+}  // extern "C"

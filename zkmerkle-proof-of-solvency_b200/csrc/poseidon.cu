@@ -1,0 +1,515 @@
+// Batched Poseidon over BN254 Fr and the fixed-depth Merkle tree on sm_100a.
+//
+// Replaces (a) the bnb-chain gnark-crypto fr/poseidon hashers -- poseidon.Poseidon / PoseidonBytes / NewPoseidon, call
+// sites src/utils/account_tree.go:19,27, src/utils/utils.go:748, src/witness/main.go:181 -- and (b)
+// FixedDepthMerkleTree.Build / GetProof, src/utils/merkletree/merkletree.go:192-279,297-308, plus the leaf hashing of
+// utils.AccountInfoToHash / ComputeUserAssetsCommitment, src/utils/utils.go:744-750,188-221.
+//
+// Permutation: x^5 S-box, R_F = 8, R_P = iden3 table, round constants and Cauchy MDS from the Grain LFSR (generated
+// here on the host at first use).  Sponge: state = [0, in...], 12 inputs per permutation, lane 0 chains, the last
+// partial chunk uses the width-(rem+1) permutation (see DESIGN.md "Poseidon parity" for what is pinned).
+// Kernels: 2-to-1 node hash = one thread per node (t = 3 state in registers); wide hashes = 16 lanes per hash, one
+// state element per lane, MDS row-times-vector with warp shuffles.
+#include "internal.h"
+
+using namespace ff;
+
+namespace zk {
+
+static const int MAX_T = 13;
+static const int ROUNDS_P_TABLE[16] = {56, 57, 56, 60, 60, 63, 64, 63, 60, 66, 60, 65, 70, 60, 64, 68};
+
+struct PoseidonTables { const Fr *rc[MAX_T + 1]; const Fr *mds[MAX_T + 1]; int rp[MAX_T + 1]; };
+struct PoseidonState { PoseidonTables tab; Fr *blob = nullptr; };
+
+// ------------------------------------------------------------------------------------------------ constants (host)
+namespace {
+struct Grain {
+    uint8_t s[80];
+    int clock() { int nb = s[62] ^ s[51] ^ s[38] ^ s[23] ^ s[13] ^ s[0]; memmove(s, s + 1, 79); s[79] = (uint8_t)nb; return nb; }
+    Grain(int t, int rf, int rp) {
+        int pos = 0;
+        auto put = [&](int v, int w) { for (int i = w - 1; i >= 0; i--) s[pos++] = (v >> i) & 1; };
+        put(1, 2); put(0, 4); put(254, 12); put(t, 12); put(rf, 10); put(rp, 10);
+        while (pos < 80) s[pos++] = 1;
+        for (int i = 0; i < 160; i++) clock();
+    }
+    int bit() { for (;;) { int a = clock(), b = clock(); if (a) return b; } }
+    Fr draw() {   // 254 bits, MSB first, as a plain integer
+        Fr v = Fr::zero();
+        for (int i = 0; i < 254; i++) {
+            for (int k = 7; k > 0; k--) v.l[k] = (v.l[k] << 1) | (v.l[k - 1] >> 31);
+            v.l[0] = (v.l[0] << 1) | (uint32_t)bit();
+        }
+        return v;
+    }
+};
+bool geq_modulus(const Fr &v) {
+    for (int i = 7; i >= 0; i--) { if (v.l[i] > FrParams::M(i)) return true; if (v.l[i] < FrParams::M(i)) return false; }
+    return true;
+}
+}  // namespace
+
+static void build_constants(int t, std::vector<Fr> &rc, std::vector<Fr> &mds, int &rp) {
+    rp = ROUNDS_P_TABLE[t - 2];
+    Grain g(t, 8, rp);
+    rc.clear(); mds.assign((size_t)t * t, Fr::zero());
+    while ((int)rc.size() < (8 + rp) * t) { Fr v = g.draw(); if (!geq_modulus(v)) rc.push_back(Fr::to_mont(v)); }
+    for (;;) {
+        std::vector<Fr> xy(2 * t);
+        for (auto &e : xy) { Fr v = g.draw(); if (geq_modulus(v)) v = Fr::reduce_once(v); e = Fr::to_mont(v); }
+        bool ok = true;
+        for (int i = 0; i < 2 * t && ok; i++) for (int j = 0; j < i; j++) if (xy[i] == xy[j]) { ok = false; break; }
+        for (int i = 0; i < t && ok; i++) for (int j = 0; j < t; j++) {
+            Fr s = Fr::add(xy[i], xy[t + j]);
+            if (s.is_zero()) { ok = false; break; }
+            mds[(size_t)i * t + j] = Fr::inv(s);
+        }
+        if (ok) return;
+    }
+}
+
+static int32_t get_tables(zkpor_ctx *ctx, PoseidonTables *out) {
+    if (!ctx->pos_consts) {
+        PoseidonState *st = new PoseidonState();
+        std::vector<Fr> all;
+        size_t rc_off[MAX_T + 1] = {0}, mds_off[MAX_T + 1] = {0};
+        for (int t = 2; t <= MAX_T; t++) {
+            std::vector<Fr> rc, mds; int rp;
+            build_constants(t, rc, mds, rp);
+            st->tab.rp[t] = rp;
+            rc_off[t] = all.size(); all.insert(all.end(), rc.begin(), rc.end());
+            mds_off[t] = all.size(); all.insert(all.end(), mds.begin(), mds.end());
+        }
+        cudaError_t e = cudaMalloc((void **)&st->blob, all.size() * sizeof(Fr));
+        if (e != cudaSuccess) { delete st; set_error("cudaMalloc poseidon tables: %s", cudaGetErrorString(e)); return ZKPOR_ERR_OOM; }
+        e = cudaMemcpy(st->blob, all.data(), all.size() * sizeof(Fr), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(st->blob); delete st; set_error("poseidon tables upload: %s", cudaGetErrorString(e)); return ZKPOR_ERR_CUDA; }
+        for (int t = 0; t <= MAX_T; t++) {
+            st->tab.rc[t] = t >= 2 ? st->blob + rc_off[t] : nullptr;
+            st->tab.mds[t] = t >= 2 ? st->blob + mds_off[t] : nullptr;
+            if (t < 2) st->tab.rp[t] = 0;
+        }
+        ctx->pos_consts = st;
+    }
+    *out = ((PoseidonState *)ctx->pos_consts)->tab;
+    return ZKPOR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ Fr sbox5(const Fr &x) { Fr x2 = Fr::sqr(x); return Fr::mul(Fr::sqr(x2), x); }
+
+// 32-byte big-endian canonical -> Montgomery
+__device__ __forceinline__ Fr load_be_mont(const uint8_t *p) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
+    Fr v;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v.l[i] = __byte_perm(w[7 - i], 0, 0x0123);
+    return Fr::to_mont(v);
+}
+__device__ __forceinline__ void store_be_plain(uint8_t *p, const Fr &mont) {
+    Fr v = Fr::from_mont(mont);
+    uint32_t *w = reinterpret_cast<uint32_t *>(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[7 - i] = __byte_perm(v.l[i], 0, 0x0123);
+}
+
+// t = 3 permutation, whole state in registers
+__device__ __forceinline__ void permute3(Fr &s0, Fr &s1, Fr &s2, const Fr *__restrict__ rc, const Fr *__restrict__ mds, int rp) {
+    Fr m[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) m[k] = mds[k];
+    const int rounds = 8 + rp;
+    for (int r = 0; r < rounds; r++) {
+        s0 = Fr::add(s0, rc[3 * r]); s1 = Fr::add(s1, rc[3 * r + 1]); s2 = Fr::add(s2, rc[3 * r + 2]);
+        s0 = sbox5(s0);
+        if (r < 4 || r >= 4 + rp) { s1 = sbox5(s1); s2 = sbox5(s2); }
+        Fr n0 = Fr::add(Fr::add(Fr::mul(m[0], s0), Fr::mul(m[1], s1)), Fr::mul(m[2], s2));
+        Fr n1 = Fr::add(Fr::add(Fr::mul(m[3], s0), Fr::mul(m[4], s1)), Fr::mul(m[5], s2));
+        Fr n2 = Fr::add(Fr::add(Fr::mul(m[6], s0), Fr::mul(m[7], s1)), Fr::mul(m[8], s2));
+        s0 = n0; s1 = n1; s2 = n2;
+    }
+}
+
+__device__ __forceinline__ Fr shfl_fr(const Fr &v, int src) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src, 16);
+    return r;
+}
+
+// Width-t permutation spread over a 16-lane group: lane i owns state[i] (lanes >= t carry garbage, never read).
+__device__ __forceinline__ Fr group_permute(Fr s, int t, int lane, const PoseidonTables &tab) {
+    const Fr *__restrict__ rc = tab.rc[t];
+    const Fr *__restrict__ row = tab.mds[t] + (lane < t ? lane : 0) * t;
+    const int rp = tab.rp[t], rounds = 8 + rp;
+    const int li = lane < t ? lane : 0;
+    for (int r = 0; r < rounds; r++) {
+        s = Fr::add(s, rc[r * t + li]);
+        if (r < 4 || r >= 4 + rp || lane == 0) s = sbox5(s);
+        Fr acc = Fr::zero();
+        for (int j = 0; j < t; j++) acc = Fr::add(acc, Fr::mul(row[j], shfl_fr(s, j)));
+        s = acc;
+    }
+    return s;
+}
+
+// poseidon.Poseidon(inputs...) by a 16-lane group; `input(k)` yields the k-th input in Montgomery form.
+template <class In>
+__device__ __forceinline__ Fr group_hash(In input, uint32_t n_in, int lane, const PoseidonTables &tab, int out_lane) {
+    Fr s = Fr::zero();
+    uint32_t start = 0;
+    int width = MAX_T;
+    for (uint32_t i = 0; i < n_in / 12 && n_in > 12; i++) {
+        if (lane >= 1 && lane <= 12) s = input(start + lane - 1);
+        s = group_permute(s, 13, lane, tab);
+        start += 12;
+    }
+    if (start < n_in) {
+        int rem = (int)(n_in - start);
+        if (lane >= 1 && lane <= rem) s = input(start + lane - 1);
+        s = group_permute(s, rem + 1, lane, tab);
+        width = rem + 1;
+    }
+    return shfl_fr(s, out_lane < width ? out_lane : 0);
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+// generic batch: `count` hashes of n_in big-endian elements
+__global__ void __launch_bounds__(128) k_hash_batch(const uint8_t *__restrict__ in, uint32_t n_in, uint64_t count, uint8_t *__restrict__ out,
+                                                    PoseidonTables tab, int out_lane) {
+    uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    int lane = threadIdx.x & 15;
+    bool live = g < count;
+    uint64_t gi = live ? g : count - 1;
+    const uint8_t *base = in + gi * n_in * 32;
+    Fr h = group_hash([&](uint32_t k) { return load_be_mont(base + 32 * (size_t)k); }, n_in, lane, tab, out_lane);
+    if (live && lane == 0) store_be_plain(out + g * 32, h);
+}
+
+// utils.AccountInfoToHash for accounts of one tier; flat = n x tier*6 u64 (PaddingAccountAssets layout)
+__global__ void __launch_bounds__(128) k_account_leaves(const uint8_t *__restrict__ ids, const uint8_t *__restrict__ totals,
+                                                        const uint64_t *__restrict__ flat, uint64_t n, uint32_t tier, uint8_t *__restrict__ out,
+                                                        PoseidonTables tab, int out_lane) {
+    uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    int lane = threadIdx.x & 15;
+    bool live = g < n;
+    uint64_t gi = live ? g : n - 1;
+    const uint32_t nflat = tier * 6, nel = (nflat + 2) / 3;
+    const uint64_t *f = flat + gi * nflat;
+    // packed triple a*2^128 + b*2^64 + c (src/utils/utils.go:196-218); < 2^192 < r
+    Fr commit = group_hash([&](uint32_t k) {
+        Fr v = Fr::zero();
+        uint64_t a = f[3 * k], b = 3 * k + 1 < nflat ? f[3 * k + 1] : 0, c = 3 * k + 2 < nflat ? f[3 * k + 2] : 0;
+        v.l[0] = (uint32_t)c; v.l[1] = (uint32_t)(c >> 32); v.l[2] = (uint32_t)b; v.l[3] = (uint32_t)(b >> 32);
+        v.l[4] = (uint32_t)a; v.l[5] = (uint32_t)(a >> 32);
+        return Fr::to_mont(v);
+    }, nel, lane, tab, out_lane);
+    const uint8_t *id = ids + gi * 32, *tot = totals + gi * 96;
+    Fr h = group_hash([&](uint32_t k) { return k == 0 ? load_be_mont(id) : k < 4 ? load_be_mont(tot + 32 * (k - 1)) : commit; },
+                      5, lane, tab, out_lane);
+    if (live && lane == 0) store_be_plain(out + g * 32, h);
+}
+
+// one Merkle level: node p of `cur` from children 2p, 2p+1 of `prev`; non-dirty children read as nil_prev,
+// a node with no dirty child becomes nil_cur (what getNodeAt returns for it) and stays non-dirty.
+__global__ void __launch_bounds__(128) k_merkle_level(const uint8_t *__restrict__ prev, const uint8_t *__restrict__ prev_dirty, uint64_t prev_len,
+                                                      uint8_t *__restrict__ cur, uint8_t *__restrict__ cur_dirty, uint64_t cur_len,
+                                                      const uint8_t *__restrict__ nil_prev, const uint8_t *__restrict__ nil_cur,
+                                                      PoseidonTables tab, int out_lane) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= cur_len) return;
+    uint64_t lc = 2 * p, rc_ = 2 * p + 1;
+    bool dl = lc < prev_len && prev_dirty[lc], dr = rc_ < prev_len && prev_dirty[rc_];
+    uint4 *dst = reinterpret_cast<uint4 *>(cur + 32 * p);
+    if (!dl && !dr) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(nil_cur);
+        dst[0] = s[0]; dst[1] = s[1]; cur_dirty[p] = 0;
+        return;
+    }
+    Fr s0 = Fr::zero(), s1 = load_be_mont(dl ? prev + 32 * lc : nil_prev), s2 = load_be_mont(dr ? prev + 32 * rc_ : nil_prev);
+    permute3(s0, s1, s2, tab.rc[3], tab.mds[3], tab.rp[3]);
+    store_be_plain(cur + 32 * p, out_lane == 0 ? s0 : out_lane == 1 ? s1 : s2);
+    cur_dirty[p] = 1;
+}
+
+// 2-to-1 hashes of arbitrary pairs (used for the nil chain and by tests): out[i] = H(in[2i], in[2i+1])
+__global__ void k_node_pairs(const uint8_t *__restrict__ in, uint64_t count, uint8_t *__restrict__ out, PoseidonTables tab, int out_lane) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fr s0 = Fr::zero(), s1 = load_be_mont(in + 64 * i), s2 = load_be_mont(in + 64 * i + 32);
+    permute3(s0, s1, s2, tab.rc[3], tab.mds[3], tab.rp[3]);
+    store_be_plain(out + 32 * i, out_lane == 0 ? s0 : out_lane == 1 ? s1 : s2);
+}
+
+// nil[l] = H(nil[l-1], nil[l-1]), sequential (depth <= 32): one thread
+__global__ void k_nil_chain(uint8_t *nil, uint32_t depth, PoseidonTables tab, int out_lane) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (uint32_t l = 1; l <= depth; l++) {
+        Fr s0 = Fr::zero(), s1 = load_be_mont(nil + 32 * (l - 1)), s2 = s1;
+        permute3(s0, s1, s2, tab.rc[3], tab.mds[3], tab.rp[3]);
+        store_be_plain(nil + 32 * l, out_lane == 0 ? s0 : out_lane == 1 ? s1 : s2);
+    }
+}
+
+__global__ void k_set_keys(uint8_t *__restrict__ leaves, uint8_t *__restrict__ dirty, const uint32_t *__restrict__ keys, uint64_t count,
+                           const uint8_t *__restrict__ vals) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t k = keys[i];
+    const uint4 *s = reinterpret_cast<const uint4 *>(vals + 32 * i);
+    uint4 *d = reinterpret_cast<uint4 *>(leaves + 32 * (size_t)k);
+    d[0] = s[0]; d[1] = s[1]; dirty[k] = 1;
+}
+
+struct TreeDev { const uint8_t *node[33]; const uint8_t *dirty[33]; uint64_t len[33]; const uint8_t *nil; uint32_t depth; };
+
+// out[(i*depth + l)] = sibling of key i at level l (GetProof, merkletree.go:297-308)
+__global__ void k_get_proofs(TreeDev t, const uint32_t *__restrict__ keys, uint64_t count, uint8_t *__restrict__ out) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * t.depth) return;
+    uint32_t l = (uint32_t)(idx % t.depth);
+    uint64_t i = idx / t.depth;
+    uint64_t sib = ((uint64_t)keys[i] >> l) ^ 1;
+    const uint8_t *src = (sib < t.len[l] && t.dirty[l][sib]) ? t.node[l] + 32 * sib : t.nil + 32 * l;
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(out + 32 * idx);
+    d[0] = s[0]; d[1] = s[1];
+}
+__global__ void k_get_leaves(TreeDev t, const uint32_t *__restrict__ keys, uint64_t count, uint8_t *__restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint64_t k = keys[i];
+    const uint8_t *src = (k < t.len[0] && t.dirty[0][k]) ? t.node[0] + 32 * k : t.nil;
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(out + 32 * i);
+    d[0] = s[0]; d[1] = s[1];
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+struct zkpor_tree {
+    uint32_t depth = 0;
+    uint64_t capacity = 0;
+    uint8_t *node[33] = {nullptr};    // node[0] = leaves
+    uint8_t *dirty[33] = {nullptr};
+    uint64_t len[33] = {0};
+    uint8_t *nil = nullptr;           // (depth+1) x 32 B on device
+    uint8_t nil_host[33][32];
+    uint8_t root[32];
+    bool any_set = false, built = false;
+    int out_lane = 1;
+};
+
+static TreeDev tree_dev(const zkpor_tree *t) {
+    TreeDev d;
+    for (int l = 0; l < 33; l++) { d.node[l] = t->node[l]; d.dirty[l] = t->dirty[l]; d.len[l] = t->len[l]; }
+    d.nil = t->nil; d.depth = t->depth;
+    return d;
+}
+
+extern "C" {
+
+void zk_free_poseidon(zkpor_ctx *ctx) {
+    if (!ctx->pos_consts) return;
+    PoseidonState *st = (PoseidonState *)ctx->pos_consts;
+    if (st->blob) cudaFree(st->blob);
+    delete st;
+    ctx->pos_consts = nullptr;
+}
+
+int32_t zkpor_poseidon_set_out_lane(zkpor_ctx *ctx, int32_t lane) {
+    ZK_REQUIRE(ctx != nullptr, "poseidon: null context");
+    ZK_REQUIRE(lane == 0 || lane == 1, "poseidon: output lane must be 0 or 1");
+    ctx->poseidon_out_lane = lane;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_poseidon_hash_batch(zkpor_ctx *ctx, const void *in_be, uint32_t n_in, uint64_t count, void *out_be) {
+    ZK_REQUIRE(ctx != nullptr && in_be != nullptr && out_be != nullptr, "poseidon: null argument");
+    ZK_REQUIRE(n_in >= 1, "poseidon: empty input");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    if (count == 0) return ZKPOR_OK;
+    stages_reset(ctx);
+    PoseidonTables tab; ZK_TRY(get_tables(ctx, &tab));
+    const void *din;
+    stage_begin(ctx, ST_H2D);
+    ZK_TRY(to_device(ctx, in_be, (size_t)count * n_in * 32, ctx->io, &din));
+    stage_end(ctx, ST_H2D);
+    const bool out_dev = is_device_ptr(out_be);
+    uint8_t *dout = (uint8_t *)out_be;
+    if (!out_dev) { ZK_TRY(ctx->misc.reserve(count * 32)); dout = ctx->misc.as<uint8_t>(); }
+    stage_begin(ctx, ST_POSEIDON);
+    ZK_LAUNCH(ctx, k_hash_batch, grid_for(count * 16, 128), 128, 0, (const uint8_t *)din, n_in, count, dout, tab, ctx->poseidon_out_lane);
+    stage_end(ctx, ST_POSEIDON);
+    if (!out_dev) {
+        stage_begin(ctx, ST_D2H);
+        ZK_CUDA(cudaMemcpyAsync(out_be, dout, count * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        stage_end(ctx, ST_D2H);
+    }
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    stages_collect(ctx);
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_account_leaves(zkpor_ctx *ctx, const void *ids_be, const void *totals_be, const void *flat_assets, uint64_t n,
+                             uint32_t tier, void *out_be) {
+    ZK_REQUIRE(ctx != nullptr && ids_be && totals_be && flat_assets && out_be, "account_leaves: null argument");
+    ZK_REQUIRE(tier >= 1 && tier <= 4096, "account_leaves: tier out of range");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return ZKPOR_OK;
+    stages_reset(ctx);
+    PoseidonTables tab; ZK_TRY(get_tables(ctx, &tab));
+    const void *d_ids, *d_tot, *d_flat;
+    stage_begin(ctx, ST_H2D);
+    ZK_TRY(to_device(ctx, ids_be, n * 32, ctx->in_scalars, &d_ids));
+    ZK_TRY(to_device(ctx, totals_be, n * 96, ctx->io, &d_tot));
+    ZK_TRY(to_device(ctx, flat_assets, n * (size_t)tier * 48, ctx->in_points, &d_flat));
+    stage_end(ctx, ST_H2D);
+    const bool out_dev = is_device_ptr(out_be);
+    uint8_t *dout = (uint8_t *)out_be;
+    if (!out_dev) { ZK_TRY(ctx->misc.reserve(n * 32)); dout = ctx->misc.as<uint8_t>(); }
+    stage_begin(ctx, ST_POSEIDON);
+    ZK_LAUNCH(ctx, k_account_leaves, grid_for(n * 16, 128), 128, 0, (const uint8_t *)d_ids, (const uint8_t *)d_tot, (const uint64_t *)d_flat, n,
+              tier, dout, tab, ctx->poseidon_out_lane);
+    stage_end(ctx, ST_POSEIDON);
+    if (!out_dev) {
+        stage_begin(ctx, ST_D2H);
+        ZK_CUDA(cudaMemcpyAsync(out_be, dout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        stage_end(ctx, ST_D2H);
+    }
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    stages_collect(ctx);
+    return ZKPOR_OK;
+}
+
+// ---- tree ------------------------------------------------------------------------------------------------------
+int32_t zkpor_tree_free(zkpor_ctx *ctx, zkpor_tree *t) {
+    (void)ctx;
+    if (!t) return ZKPOR_OK;
+    for (int l = 0; l < 33; l++) { if (t->node[l]) cudaFree(t->node[l]); if (t->dirty[l]) cudaFree(t->dirty[l]); }
+    if (t->nil) cudaFree(t->nil);
+    delete t;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_tree_create(zkpor_ctx *ctx, uint32_t depth, const uint8_t nil_leaf[32], uint64_t capacity, zkpor_tree **out) {
+    ZK_REQUIRE(ctx != nullptr && nil_leaf != nullptr && out != nullptr, "tree_create: null argument");
+    // merkletree.go:138-146 panics; the C-ABI reports
+    ZK_REQUIRE(depth <= 32, "depth too large");
+    ZK_REQUIRE(depth > 0, "depth must be positive");
+    ZK_REQUIRE(capacity <= (1ull << depth), "capacity exceeds maximum for given depth");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    PoseidonTables tab; ZK_TRY(get_tables(ctx, &tab));
+    zkpor_tree *t = new zkpor_tree();
+    t->depth = depth; t->capacity = capacity; t->out_lane = ctx->poseidon_out_lane;
+    auto fail = [&](int32_t rc) { zkpor_tree_free(ctx, t); return rc; };
+    for (uint32_t l = 0; l <= depth; l++) {
+        uint64_t len = l == 0 ? capacity : (capacity + ((1ull << l) - 1)) >> l;
+        if (l > 0 && len == 0) len = 1;
+        t->len[l] = len;
+        size_t nbytes = (size_t)(len ? len : 1);
+        if (cudaMalloc((void **)&t->node[l], nbytes * 32) != cudaSuccess || cudaMalloc((void **)&t->dirty[l], nbytes) != cudaSuccess) {
+            set_error("tree_create: out of device memory at level %u", l); return fail(ZKPOR_ERR_OOM);
+        }
+        if (cudaMemsetAsync(t->dirty[l], 0, nbytes, ctx->stream) != cudaSuccess) { set_error("tree_create: memset failed"); return fail(ZKPOR_ERR_CUDA); }
+    }
+    if (cudaMalloc((void **)&t->nil, 33 * 32) != cudaSuccess) { set_error("tree_create: out of device memory"); return fail(ZKPOR_ERR_OOM); }
+    if (cudaMemcpyAsync(t->nil, nil_leaf, 32, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { set_error("tree_create: copy failed"); return fail(ZKPOR_ERR_CUDA); }
+    k_nil_chain<<<1, 32, 0, ctx->stream>>>(t->nil, depth, tab, t->out_lane);
+    ctx->launches++;
+    if (cudaMemcpyAsync(t->nil_host, t->nil, 32 * (depth + 1), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("tree_create: nil chain failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(ZKPOR_ERR_CUDA); }
+    memcpy(t->root, t->nil_host[depth], 32);
+    *out = t;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_tree_set_range(zkpor_ctx *ctx, zkpor_tree *t, uint64_t first_key, uint64_t count, const void *leaves_be) {
+    ZK_REQUIRE(ctx && t && (leaves_be || count == 0), "tree_set: null argument");
+    if (first_key + count > t->capacity) { set_error("key %llu out of range for capacity %llu", (unsigned long long)(first_key + count - 1), (unsigned long long)t->capacity); return ZKPOR_ERR_INVALID_ARG; }
+    if (count == 0) return ZKPOR_OK;
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    ZK_CUDA(cudaMemcpyAsync(t->node[0] + 32 * first_key, leaves_be, count * 32, cudaMemcpyDefault, ctx->stream));
+    ZK_CUDA(cudaMemsetAsync(t->dirty[0] + first_key, 1, count, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    t->any_set = true; t->built = false;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_tree_set_keys(zkpor_ctx *ctx, zkpor_tree *t, const uint32_t *keys, uint64_t count, const void *leaves_be) {
+    ZK_REQUIRE(ctx && t && ((keys && leaves_be) || count == 0), "tree_set: null argument");
+    if (count == 0) return ZKPOR_OK;
+    ZK_REQUIRE(!is_device_ptr(keys), "tree_set_keys: keys must be a host array");
+    for (uint64_t i = 0; i < count; i++)
+        if (keys[i] >= t->capacity) { set_error("key %u out of range for capacity %llu", keys[i], (unsigned long long)t->capacity); return ZKPOR_ERR_INVALID_ARG; }
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    const void *dk, *dv;
+    ZK_TRY(to_device(ctx, keys, count * 4, ctx->in_scalars, &dk));
+    ZK_TRY(to_device(ctx, leaves_be, count * 32, ctx->io, &dv));
+    ZK_LAUNCH(ctx, k_set_keys, grid_for(count, 256), 256, 0, t->node[0], t->dirty[0], (const uint32_t *)dk, count, (const uint8_t *)dv);
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    t->any_set = true; t->built = false;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_tree_build(zkpor_ctx *ctx, zkpor_tree *t) {
+    ZK_REQUIRE(ctx && t, "tree_build: null argument");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    stages_reset(ctx);
+    PoseidonTables tab; ZK_TRY(get_tables(ctx, &tab));
+    if (t->any_set) {
+        stage_begin(ctx, ST_POSEIDON);
+        for (uint32_t l = 1; l <= t->depth; l++) {
+            ZK_LAUNCH(ctx, k_merkle_level, grid_for(t->len[l], 128), 128, 0, (const uint8_t *)t->node[l - 1], (const uint8_t *)t->dirty[l - 1],
+                      t->len[l - 1], t->node[l], t->dirty[l], t->len[l], (const uint8_t *)(t->nil + 32 * (l - 1)),
+                      (const uint8_t *)(t->nil + 32 * l), tab, t->out_lane);
+        }
+        stage_end(ctx, ST_POSEIDON);
+        ZK_CUDA(cudaMemcpyAsync(t->root, t->node[t->depth], 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    stages_collect(ctx);
+    t->built = true;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_tree_root(zkpor_ctx *ctx, zkpor_tree *t, uint8_t out_root[32]) {
+    ZK_REQUIRE(ctx && t && out_root, "tree_root: null argument");
+    memcpy(out_root, t->root, 32);
+    return ZKPOR_OK;
+}
+
+static int32_t tree_gather(zkpor_ctx *ctx, zkpor_tree *t, const uint32_t *keys, uint64_t count, void *out_be, bool proofs) {
+    ZK_REQUIRE(ctx && t && ((keys && out_be) || count == 0), "tree_get: null argument");
+    if (count == 0) return ZKPOR_OK;
+    ZK_REQUIRE(!is_device_ptr(keys), "tree_get: keys must be a host array");
+    for (uint64_t i = 0; i < count; i++)
+        if ((uint64_t)keys[i] >= (1ull << t->depth)) { set_error("key %u out of range for tree depth %u", keys[i], t->depth); return ZKPOR_ERR_INVALID_ARG; }
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    const void *dk;
+    ZK_TRY(to_device(ctx, keys, count * 4, ctx->in_scalars, &dk));
+    const size_t per = proofs ? (size_t)t->depth * 32 : 32, bytes = per * count;
+    const bool out_dev = is_device_ptr(out_be);
+    uint8_t *dout = (uint8_t *)out_be;
+    if (!out_dev) { ZK_TRY(ctx->misc.reserve(bytes)); dout = ctx->misc.as<uint8_t>(); }
+    TreeDev td = tree_dev(t);
+    if (proofs) ZK_LAUNCH(ctx, k_get_proofs, grid_for(count * t->depth, 256), 256, 0, td, (const uint32_t *)dk, count, dout);
+    else ZK_LAUNCH(ctx, k_get_leaves, grid_for(count, 256), 256, 0, td, (const uint32_t *)dk, count, dout);
+    if (!out_dev) ZK_CUDA(cudaMemcpyAsync(out_be, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKPOR_OK;
+}
+int32_t zkpor_tree_get_proofs(zkpor_ctx *ctx, zkpor_tree *t, const uint32_t *keys, uint64_t count, void *out_be) { return tree_gather(ctx, t, keys, count, out_be, true); }
+int32_t zkpor_tree_get_leaves(zkpor_ctx *ctx, zkpor_tree *t, const uint32_t *keys, uint64_t count, void *out_be) { return tree_gather(ctx, t, keys, count, out_be, false); }
+
+int32_t zkpor_tree_level(zkpor_ctx *ctx, zkpor_tree *t, uint32_t level, void **out_dev_ptr, uint64_t *out_len) {
+    ZK_REQUIRE(ctx && t && out_dev_ptr && out_len, "tree_level: null argument");
+    ZK_REQUIRE(level <= t->depth, "tree_level: level out of range");
+    *out_dev_ptr = t->node[level]; *out_len = t->len[level];
+    return ZKPOR_OK;
+}
+
+}  // extern "C"
