@@ -154,6 +154,13 @@ int32_t zkpor_tree_get_proofs(zkpor_ctx *ctx, zkpor_tree *t, const uint32_t *key
 /* device pointer of level `level` (0 = leaves) and its length in nodes, for multi-GPU subtree exchange */
 int32_t zkpor_tree_level(zkpor_ctx *ctx, zkpor_tree *t, uint32_t level, void **out_dev_ptr, uint64_t *out_len);
 
+/* ---- synthetic workloads (bench / full-size parity tooling; not on the proving path) ----------------------------
+ * points[i] = (k0 + i*d) * G with known discrete logs, written as affine Montgomery points into DEVICE memory;
+ * scalars = counter-based uniform Fr (kind 0) or the witness-like mix of SURVEY.md 8(d) (kind 1). */
+int32_t zkpor_synth_points_g1(zkpor_ctx *ctx, const uint8_t k0_be[32], const uint8_t d_be[32], uint64_t n, void *out_dev);
+int32_t zkpor_synth_points_g2(zkpor_ctx *ctx, const uint8_t k0_be[32], const uint8_t d_be[32], uint64_t n, void *out_dev);
+int32_t zkpor_synth_scalars(zkpor_ctx *ctx, uint64_t seed, uint64_t n, int32_t kind, void *out_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,11 @@ int  orc_g2_on_curve(const uint64_t *p);
 void orc_ntt(uint64_t *data_mont, int logn, int inverse, int dit, int coset, int threads);
 void orc_compute_h(const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t m, int logn, uint64_t *out_h, int threads);
 
+/* full-size check helpers */
+void orc_fr_index_sums(const uint64_t *v, size_t n, uint64_t *out_sum, uint64_t *out_isum, int threads);
+void orc_eval_barycentric(const uint64_t *evals_mont, size_t m, int logn, const uint64_t *x0_mont, uint64_t *out_mont, int threads);
+void orc_poly_eval_bitrev(const uint64_t *coef_mont, int logn, const uint64_t *x0_mont, uint64_t *out_mont, int threads);
+
 /* Poseidon / Merkle */
 void orc_poseidon_set_out_lane(int lane);
 int  orc_poseidon_get_out_lane(void);

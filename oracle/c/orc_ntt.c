@@ -106,3 +106,80 @@ void orc_compute_h(const uint64_t *a_in, const uint64_t *b_in, const uint64_t *c
     orc_ntt((uint64_t *)a, logn, 1, 0, 1, threads);
     free(b); free(c);
 }
+
+/* ---- full-size check helpers (tests of the 2^26 configurations): O(n) field work, threaded ---- */
+/* out_sum = sum_i v_i, out_isum = sum_i i*v_i, the limb patterns v_i taken as integers mod r */
+void orc_fr_index_sums(const uint64_t *v, size_t n, uint64_t *out_sum, uint64_t *out_isum, int threads) {
+    if (threads <= 0) threads = omp_get_max_threads();
+    fe S, I; memset(&S, 0, sizeof S); memset(&I, 0, sizeof I);
+    #pragma omp parallel num_threads(threads)
+    {
+        fe s, t; memset(&s, 0, sizeof s); memset(&t, 0, sizeof t);
+        #pragma omp for schedule(static)
+        for (size_t i = 0; i < n; i++) {
+            const fe *x = (const fe *)(v + 4 * i);
+            fe im, p; fr_from_u64(&im, (uint64_t)i);
+            fr_add(&s, &s, x); fr_mul(&p, x, &im); fr_add(&t, &t, &p);
+        }
+        #pragma omp critical
+        { fr_add(&S, &S, &s); fr_add(&I, &I, &t); }
+    }
+    memcpy(out_sum, &S, 32); memcpy(out_isum, &I, 32);
+}
+/* P(x0) for P given by its evaluations on the size-2^logn subgroup (Montgomery in/out):
+ * P(x0) = (x0^n - 1)/n * sum_k e_k w^k / (x0 - w^k); x0 must not be in the subgroup.  Batch inversion per thread. */
+void orc_eval_barycentric(const uint64_t *evals, size_t m, int logn, const uint64_t *x0, uint64_t *out, int threads) {
+    if (threads <= 0) threads = omp_get_max_threads();
+    size_t n = (size_t)1 << logn;
+    fe g, x, acc_total; domain_gen(&g, logn); memcpy(&x, x0, 32); memset(&acc_total, 0, sizeof acc_total);
+    #pragma omp parallel num_threads(threads)
+    {
+        int T = omp_get_num_threads(), t = omp_get_thread_num();
+        size_t per = (m + T - 1) / T, lo = (size_t)t * per, hi = lo + per > m ? m : lo + per;
+        fe acc; memset(&acc, 0, sizeof acc);
+        if (lo < hi) {
+            enum { B = 1024 };
+            fe wk, e; fe_one(&wk, &ORC_FR);
+            uint64_t ex[4] = {lo, 0, 0, 0}; fe_pow(&wk, &g, ex, &ORC_FR);
+            fe den[B], pre[B], num[B];
+            for (size_t s0 = lo; s0 < hi; s0 += B) {
+                size_t cnt = hi - s0 < B ? hi - s0 : B;
+                fe run; fr_one(&run);
+                for (size_t j = 0; j < cnt; j++) {
+                    fr_sub(&den[j], &x, &wk); pre[j] = run; fr_mul(&run, &run, &den[j]);
+                    fr_mul(&num[j], (const fe *)(evals + 4 * (s0 + j)), &wk); fr_mul(&wk, &wk, &g);
+                }
+                fe inv; fr_inv(&inv, &run);
+                for (size_t j = cnt; j-- > 0;) { fr_mul(&e, &inv, &pre[j]); fr_mul(&inv, &inv, &den[j]); fr_mul(&e, &e, &num[j]); fr_add(&acc, &acc, &e); }
+            }
+        }
+        #pragma omp critical
+        fr_add(&acc_total, &acc_total, &acc);
+    }
+    fe xn = x, one, ninv; fr_one(&one);
+    for (int i = 0; i < logn; i++) fr_sqr(&xn, &xn);
+    fr_sub(&xn, &xn, &one); fr_from_u64(&ninv, (uint64_t)n); fr_inv(&ninv, &ninv);
+    fr_mul(&acc_total, &acc_total, &xn); fr_mul(&acc_total, &acc_total, &ninv);
+    memcpy(out, &acc_total, 32);
+}
+/* sum_i c_{bitrev(i)}... : evaluates the polynomial whose coefficient bitrev(pos) is stored at pos (computeH output) */
+void orc_poly_eval_bitrev(const uint64_t *coef, int logn, const uint64_t *x0, uint64_t *out, int threads) {
+    if (threads <= 0) threads = omp_get_max_threads();
+    size_t n = (size_t)1 << logn;
+    fe x, total; memcpy(&x, x0, 32); memset(&total, 0, sizeof total);
+    /* thread t takes coefficient range [lo, hi): Horner on the range, times x^lo */
+    #pragma omp parallel num_threads(threads)
+    {
+        int T = omp_get_num_threads(), t = omp_get_thread_num();
+        size_t per = (n + T - 1) / T, lo = (size_t)t * per, hi = lo + per > n ? n : lo + per;
+        if (lo < hi) {
+            fe acc; memset(&acc, 0, sizeof acc);
+            for (size_t i = hi; i-- > lo;) { fr_mul(&acc, &acc, &x); fr_add(&acc, &acc, (const fe *)(coef + 4 * bitrev(i, logn))); }
+            fe xp; uint64_t ex[4] = {lo, 0, 0, 0}; fe_pow(&xp, &x, ex, &ORC_FR);
+            fr_mul(&acc, &acc, &xp);
+            #pragma omp critical
+            fr_add(&total, &total, &acc);
+        }
+    }
+    memcpy(out, &total, 32);
+}

@@ -243,3 +243,26 @@ def groth16_prove(pkarr: dict, wa, wb, wk, committed, a, b, c, r: int, s: int, t
     if rc != 0:
         raise RuntimeError(f"orc_groth16_prove failed: {rc}")
     return out.tobytes()
+
+
+def fr_index_sums(v: np.ndarray, threads=0):
+    """(sum_i v_i, sum_i i*v_i) mod r with the limb patterns taken as integers"""
+    a = np.ascontiguousarray(v, dtype=np.uint64).reshape(-1, 4)
+    s = np.zeros(4, dtype=np.uint64); t = np.zeros(4, dtype=np.uint64)
+    lib().orc_fr_index_sums(_p(a), C.c_size_t(a.shape[0]), _p(s), _p(t), C.c_int(threads))
+    return limbs_to_ints(s)[0], limbs_to_ints(t)[0]
+
+
+def eval_barycentric(evals_mont: np.ndarray, logn: int, x0: int, threads=0) -> int:
+    a = np.ascontiguousarray(evals_mont, dtype=np.uint64).reshape(-1, 4)
+    x = fr_mont([x0]); out = np.zeros(4, dtype=np.uint64)
+    lib().orc_eval_barycentric(_p(a), C.c_size_t(a.shape[0]), C.c_int(logn), _p(x), _p(out), C.c_int(threads))
+    return fr_unmont(out)[0]
+
+
+def poly_eval_bitrev(coef_mont: np.ndarray, logn: int, x0: int, threads=0) -> int:
+    a = np.ascontiguousarray(coef_mont, dtype=np.uint64).reshape(-1, 4)
+    assert a.shape[0] == 1 << logn
+    x = fr_mont([x0]); out = np.zeros(4, dtype=np.uint64)
+    lib().orc_poly_eval_bitrev(_p(a), C.c_int(logn), _p(x), _p(out), C.c_int(threads))
+    return fr_unmont(out)[0]

@@ -218,6 +218,23 @@ class Context:
         return out
 
 
+def _be_arr(v: int):
+    return (C.c_uint8 * 32).from_buffer_copy(be32(v % R_MOD))
+
+
+def synth_points_g1(ctx: Context, k0: int, d: int, n: int, out_dev):
+    """out_dev[i] = (k0 + i*d) * G1, affine Montgomery, written to device memory"""
+    _check(lib().zkpor_synth_points_g1(ctx._h, _be_arr(k0), _be_arr(d), C.c_uint64(n), _ptr(out_dev)))
+
+
+def synth_points_g2(ctx: Context, k0: int, d: int, n: int, out_dev):
+    _check(lib().zkpor_synth_points_g2(ctx._h, _be_arr(k0), _be_arr(d), C.c_uint64(n), _ptr(out_dev)))
+
+
+def synth_scalars(ctx: Context, seed: int, n: int, kind: int, out_dev):
+    _check(lib().zkpor_synth_scalars(ctx._h, C.c_uint64(seed), C.c_uint64(n), C.c_int32(kind), _ptr(out_dev)))
+
+
 def g1_sum_partials(partials: np.ndarray) -> np.ndarray:
     p = np.ascontiguousarray(partials, dtype=np.uint64).reshape(-1, 16)
     out = np.zeros(8, dtype=np.uint64)
