@@ -56,6 +56,11 @@ int32_t zkpor_ctx_stream(zkpor_ctx *ctx, void **out_stream);
  * stage names: zkpor_stage_name(i); returns the number of stages via *n. */
 int32_t zkpor_ctx_last_timings(zkpor_ctx *ctx, float *out_ms, int32_t cap, int32_t *n);
 const char *zkpor_stage_name(int32_t i);
+/* Per-launch timing of the dominant kernels (CUDA events on the context's stream around every launch of a class):
+ * enable, run, then query.  klass: 0 = G1 bucket accumulation, 1 = G2 bucket accumulation, 2 = NTT butterfly pass,
+ * 3 = digit/scatter (sort) kernels, 4 = Poseidon/Merkle kernels.  units = terms (MSM), elements (NTT), hashes. */
+int32_t zkpor_ctx_kernel_timing(zkpor_ctx *ctx, int32_t enable);
+int32_t zkpor_ctx_kernel_stats(zkpor_ctx *ctx, int32_t klass, double *total_ms, uint64_t *launches, uint64_t *units);
 
 /* ---- multi-scalar multiplication -------------------------------------------------------------------------------
  * Replaces gnark-crypto G1Jac.MultiExp / G2Jac.MultiExp (ecc/bn254/multiexp.go, out of tree) as called inside
@@ -76,6 +81,8 @@ int32_t zkpor_g2_sum_partials(const void *partials_xyzz /* host, k x 256 B */, u
  * decimation 0 = DIF (natural in, bit-reversed out), 1 = DIT (bit-reversed in, natural out); coset = OnCoset()
  * with shift 5; inverse includes the 1/n scaling.  In place over `data` (n = 2^log_n Montgomery elements). */
 int32_t zkpor_ntt(zkpor_ctx *ctx, void *data, uint32_t log_n, int32_t inverse, int32_t decimation, int32_t coset);
+/* out[i] = a[i] * b[i] in Fr (Montgomery in/out), device-resident vectors -- fr.Vector element-wise product */
+int32_t zkpor_fr_mul(zkpor_ctx *ctx, const void *a, const void *b, void *out, uint64_t n);
 /* gnark backend/groth16/bn254/prove.go computeH: a, b, c = R1CS evaluation vectors of length n_constraints,
  * zero-padded to n = 2^log_n; out_h = n elements, bit-reversed coefficient order (pairs with pk.G1.Z as gnark
  * stores it).  out_h may be host or device. */

@@ -64,6 +64,18 @@ def test_edge_cases(ctx):
     assert np.array_equal(ctx.msm_g1(pts, sc2, n), orc.g1_msm(pts, sc2))
 
 
+def test_heavy_buckets_skewed_witness(ctx):
+    """witness-like scalars at a size where one bucket (the value 1) holds far more than the heavy threshold"""
+    n = 150000
+    pts = g1_points(4096, 41); pts = np.ascontiguousarray(np.tile(pts, (n // 4096 + 1, 1))[:n])
+    sc = orc.fr_mont(rand_scalars(n, 42, "witness"))
+    assert np.array_equal(ctx.msm_g1(pts, sc, n), orc.g1_msm(pts, sc))
+    n2 = 60000
+    p2 = g2_points(1024, 43); p2 = np.ascontiguousarray(np.tile(p2, (n2 // 1024 + 1, 1))[:n2])
+    s2 = orc.fr_mont([1] * 30000 + rand_scalars(n2 - 30000, 44, "witness"))
+    assert np.array_equal(ctx.msm_g2(p2, s2, n2), orc.g2_msm(p2, s2))
+
+
 def test_device_pointer_inputs(ctx):
     import torch
     n = 5000

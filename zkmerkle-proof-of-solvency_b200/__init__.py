@@ -160,6 +160,14 @@ class Context:
         _check(lib().zkpor_ctx_last_timings(self._h, buf, 16, C.byref(n)))
         return {lib().zkpor_stage_name(i).decode(): float(buf[i]) for i in range(n.value)}
 
+    def kernel_timing(self, enable: bool):
+        _check(lib().zkpor_ctx_kernel_timing(self._h, C.c_int32(1 if enable else 0)))
+
+    def kernel_stats(self, klass: int):
+        ms, n, u = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+        _check(lib().zkpor_ctx_kernel_stats(self._h, C.c_int32(klass), C.byref(ms), C.byref(n), C.byref(u)))
+        return dict(total_ms=ms.value, launches=n.value, units=u.value)
+
     # --- MSM
     def msm_g1(self, points, scalars, n: int, flags: int = ZKPOR_SCALARS_MONT) -> np.ndarray:
         out = np.zeros(8, dtype=np.uint64)
@@ -186,6 +194,10 @@ class Context:
         """in place; data = numpy (host) or device pointer / tensor"""
         _check(lib().zkpor_ntt(self._h, _ptr(data), C.c_uint32(log_n), C.c_int32(inverse), C.c_int32(dit), C.c_int32(coset)))
         return data
+
+    def fr_mul(self, a, b, out, n: int):
+        _check(lib().zkpor_fr_mul(self._h, _ptr(a), _ptr(b), _ptr(out), C.c_uint64(n)))
+        return out
 
     def compute_h(self, a, b, c, n_constraints: int, log_n: int, out=None):
         if out is None:

@@ -37,6 +37,10 @@ const char *get_error();
 // stages whose device time is recorded per call (zkpor_ctx_last_timings)
 enum Stage { ST_H2D = 0, ST_DIGITS, ST_SORT, ST_ACCUM, ST_REDUCE, ST_NTT, ST_POSEIDON, ST_D2H, ST_COUNT };
 
+// kernel classes whose individual launches are timed with CUDA events (zkpor_ctx_kernel_stats; bench.py's roofline)
+enum KClass { KC_ACCUM_G1 = 0, KC_ACCUM_G2, KC_NTT_PASS, KC_SORT, KC_POSEIDON, KC_COUNT };
+struct KRec { int klass; uint64_t units; cudaEvent_t e0, e1; };
+
 // A grow-only device allocation reused across calls (cudaMalloc is far too slow for the hot path).
 struct DevBuf {
     void *p = nullptr;
@@ -65,7 +69,7 @@ struct zkpor_ctx {
     uint64_t launches = 0;
     int poseidon_out_lane = 1;
     // scratch
-    zk::DevBuf in_points, in_scalars, sort_idx, bucket_cnt, bucket_off, bucket_cur, buckets, partials, windows, misc, ntt_a, ntt_b, ntt_c, io;
+    zk::DevBuf in_points, in_scalars, sort_idx, bucket_cnt, bucket_off, bucket_cur, buckets, partials, windows, misc, ntt_a, ntt_b, ntt_c, io, heavy, heavy_part;
     void *pinned = nullptr; size_t pinned_cap = 0;
     // poseidon constants on device (built lazily)
     void *pos_consts = nullptr;
@@ -75,6 +79,10 @@ struct zkpor_ctx {
     cudaEvent_t ev[zk::ST_COUNT][2];
     bool ev_used[zk::ST_COUNT];
     float last_ms[zk::ST_COUNT];
+    // per-launch kernel timers
+    bool ktime_on = false;
+    std::vector<zk::KRec> klog;
+    std::vector<cudaEvent_t> ev_free;
 };
 
 namespace zk {
@@ -106,6 +114,21 @@ inline void stages_collect(zkpor_ctx *ctx) {
         if (ctx->ev_used[i]) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->ev[i][0], ctx->ev[i][1]) == cudaSuccess) ctx->last_ms[i] = ms; }
     }
 }
+
+inline cudaEvent_t kev_get(zkpor_ctx *ctx) {
+    if (!ctx->ev_free.empty()) { cudaEvent_t e = ctx->ev_free.back(); ctx->ev_free.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+// brackets one launch of a timed kernel class: KTimed kt(ctx, KC_x, units); launch; kt.stop();
+struct KTimed {
+    zkpor_ctx *ctx; KRec rec; bool on;
+    KTimed(zkpor_ctx *c, int klass, uint64_t units) : ctx(c), on(c->ktime_on) {
+        if (!on) return;
+        rec.klass = klass; rec.units = units; rec.e0 = kev_get(c); rec.e1 = kev_get(c);
+        cudaEventRecord(rec.e0, c->stream);
+    }
+    void stop() { if (!on) return; cudaEventRecord(rec.e1, ctx->stream); ctx->klog.push_back(rec); on = false; }
+};
 
 inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block); }
 

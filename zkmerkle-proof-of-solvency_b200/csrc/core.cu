@@ -90,9 +90,11 @@ int32_t zkpor_ctx_destroy(zkpor_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     zk::DevBuf *bufs[] = {&ctx->in_points, &ctx->in_scalars, &ctx->sort_idx, &ctx->bucket_cnt, &ctx->bucket_off, &ctx->bucket_cur,
-                          &ctx->buckets, &ctx->partials, &ctx->windows, &ctx->misc, &ctx->ntt_a, &ctx->ntt_b, &ctx->ntt_c, &ctx->io};
+                          &ctx->buckets, &ctx->partials, &ctx->windows, &ctx->misc, &ctx->ntt_a, &ctx->ntt_b, &ctx->ntt_c, &ctx->io, &ctx->heavy, &ctx->heavy_part};
     for (auto *b : bufs) b->release();
     zk_free_poseidon(ctx); zk_free_ntt(ctx);
+    for (auto &r : ctx->klog) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < ST_COUNT; i++) { cudaEventDestroy(ctx->ev[i][0]); cudaEventDestroy(ctx->ev[i][1]); }
     cudaStreamDestroy(ctx->stream);
@@ -113,6 +115,28 @@ int32_t zkpor_ctx_launch_count(zkpor_ctx *ctx, uint64_t *out) {
 int32_t zkpor_ctx_stream(zkpor_ctx *ctx, void **out_stream) {
     ZK_REQUIRE(ctx != nullptr && out_stream != nullptr, "ctx_stream: null argument");
     *out_stream = (void *)ctx->stream;
+    return ZKPOR_OK;
+}
+int32_t zkpor_ctx_kernel_timing(zkpor_ctx *ctx, int32_t enable) {
+    ZK_REQUIRE(ctx != nullptr, "kernel_timing: null context");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->klog) { ctx->ev_free.push_back(r.e0); ctx->ev_free.push_back(r.e1); }
+    ctx->klog.clear();
+    ctx->ktime_on = enable != 0;
+    return ZKPOR_OK;
+}
+int32_t zkpor_ctx_kernel_stats(zkpor_ctx *ctx, int32_t klass, double *total_ms, uint64_t *launches, uint64_t *units) {
+    ZK_REQUIRE(ctx != nullptr && total_ms && launches && units, "kernel_stats: null argument");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    double ms = 0; uint64_t n = 0, u = 0;
+    for (auto &r : ctx->klog) {
+        if (r.klass != klass) continue;
+        float t = 0.f; ZK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms += t; n++; u += r.units;
+    }
+    *total_ms = ms; *launches = n; *units = u;
     return ZKPOR_OK;
 }
 int32_t zkpor_ctx_last_timings(zkpor_ctx *ctx, float *out_ms, int32_t cap, int32_t *n) {

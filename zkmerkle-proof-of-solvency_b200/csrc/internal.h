@@ -11,7 +11,14 @@ MsmPlan msm_plan(uint64_t n);
 
 // Result of the scalar-side half of an MSM (digit extraction + counting sort by bucket), living in ctx scratch:
 // for window w, the signed point references of bucket b are sort_idx[w*n + off[w*nb+b] .. +cnt[w*nb+b]).
-struct MsmSorted { MsmPlan plan; uint64_t n; const uint32_t *idx, *off, *cnt; };
+// Buckets holding more than heavy_t references (skewed witnesses: the value 1 alone is ~15% of a real wire vector) are
+// cut into blocks of HEAVY_CHUNK references, each reduced by a whole CTA; see k_heavy_plan in msm.cu.
+struct HeavyBlk { uint32_t slot, start, count; };
+struct HeavyBkt { uint32_t slot, first_blk, nblk; };
+struct MsmSorted {
+    MsmPlan plan; uint64_t n; const uint32_t *idx, *off, *cnt;
+    uint32_t heavy_t, max_blks, max_bkts; const HeavyBlk *blks; const HeavyBkt *bkts; const uint32_t *counters;
+};
 
 int32_t msm_sort(zkpor_ctx *ctx, const void *d_scalars, uint64_t n, uint32_t flags, MsmSorted *out);
 int32_t msm_accumulate_g1(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, ec::G1XYZZ *host_out);

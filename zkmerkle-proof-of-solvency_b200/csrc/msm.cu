@@ -99,19 +99,82 @@ template <class F> __device__ __forceinline__ Affine<F> load_affine(const Affine
 template <class F>
 __global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict__ points, const uint32_t *__restrict__ sorted,
                                                     const uint32_t *__restrict__ off, const uint32_t *__restrict__ cnt,
-                                                    uint64_t n, MsmPlan plan, XYZZ<F> *__restrict__ buckets) {
+                                                    uint64_t n, MsmPlan plan, uint32_t heavy_t, XYZZ<F> *__restrict__ buckets) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)plan.nwin * plan.nb) return;
     uint32_t w = (uint32_t)(t / plan.nb);
     const uint32_t *idx = sorted + (size_t)w * n + off[t];
     uint32_t m = cnt[t];
+    if (m > heavy_t) return;   // reduced by k_accumulate_heavy / k_heavy_combine
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = 0; k < m; k++) {
+    if (m) {
+        // two-deep software pipeline: the reference for k+2 and the point for k+1 are in flight while k is added
+        uint32_t e = __ldg(idx), e1 = m > 1 ? __ldg(idx + 1) : 0;
+        Affine<F> p = load_affine(points + (e >> 1));
+        for (uint32_t k = 0; k < m; k++) {
+            Affine<F> pn = p; uint32_t e2 = 0;
+            if (k + 1 < m) pn = load_affine(points + (e1 >> 1));
+            if (k + 2 < m) e2 = __ldg(idx + k + 2);
+            acc.add_affine(p, e & 1);
+            p = pn; e = e1; e1 = e2;
+        }
+    }
+    buckets[t] = acc;
+}
+
+// ---- heavy buckets ----------------------------------------------------------------------------------------------
+static const uint32_t HEAVY_CHUNK = 4096;
+
+// one thread per (window, bucket): buckets above the threshold reserve ceil(cnt / HEAVY_CHUNK) block descriptors
+__global__ void k_heavy_plan(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ off, size_t slots, uint32_t heavy_t,
+                             HeavyBlk *__restrict__ blks, HeavyBkt *__restrict__ bkts, uint32_t *__restrict__ counters) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= slots) return;
+    uint32_t c = cnt[t];
+    if (c <= heavy_t) return;
+    uint32_t nblk = (c + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
+    uint32_t first = atomicAdd(&counters[0], nblk), bi = atomicAdd(&counters[1], 1u);
+    bkts[bi] = HeavyBkt{(uint32_t)t, first, nblk};
+    for (uint32_t k = 0; k < nblk; k++) {
+        uint32_t rem = c - k * HEAVY_CHUNK;
+        blks[first + k] = HeavyBlk{(uint32_t)t, off[t] + k * HEAVY_CHUNK, rem < HEAVY_CHUNK ? rem : HEAVY_CHUNK};
+    }
+}
+
+// one CTA per block descriptor: 128 strided partial sums, then a shared-memory tree
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate_heavy(const Affine<F> *__restrict__ points, const uint32_t *__restrict__ sorted,
+                                                          const HeavyBlk *__restrict__ blks, const uint32_t *__restrict__ counters,
+                                                          uint64_t n, MsmPlan plan, XYZZ<F> *__restrict__ parts) {
+    __shared__ XYZZ<F> sh[128];
+    const uint32_t b = blockIdx.x;
+    if (b >= counters[0]) return;
+    const HeavyBlk blk = blks[b];
+    const uint32_t *idx = sorted + (size_t)(blk.slot / plan.nb) * n + blk.start;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = threadIdx.x; k < blk.count; k += 128) {
         uint32_t e = __ldg(idx + k);
         Affine<F> p = load_affine(points + (e >> 1));
         acc.add_affine(p, e & 1);
     }
-    buckets[t] = acc;
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = 64; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { XYZZ<F> a = sh[threadIdx.x]; a.add(sh[threadIdx.x + s]); sh[threadIdx.x] = a; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) parts[b] = sh[0];
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_heavy_combine(const XYZZ<F> *__restrict__ parts, const HeavyBkt *__restrict__ bkts,
+                                                       const uint32_t *__restrict__ counters, XYZZ<F> *__restrict__ buckets) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counters[1]) return;
+    const HeavyBkt bk = bkts[i];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = 0; k < bk.nblk; k++) acc.add(parts[bk.first_blk + k]);
+    buckets[bk.slot] = acc;
 }
 
 // thread (w, seg): sum_{j in seg} (j+1) * B[w][j]  via running sums, segment length L
@@ -159,12 +222,30 @@ int32_t msm_sort(zkpor_ctx *ctx, const void *d_scalars, uint64_t n, uint32_t fla
         plain = ctx->misc.as<uint32_t>();
     }
     ZK_CUDA(cudaMemsetAsync(ctx->bucket_cnt.p, 0, slots * 4, ctx->stream));
-    ZK_LAUNCH(ctx, k_digits<0>, grid_for(n, 256), 256, 0, plain, n, plan, ctx->bucket_cnt.as<uint32_t>(), (uint32_t *)nullptr);
+    { KTimed kt(ctx, KC_SORT, n);
+      ZK_LAUNCH(ctx, k_digits<0>, grid_for(n, 256), 256, 0, plain, n, plan, ctx->bucket_cnt.as<uint32_t>(), (uint32_t *)nullptr);
+      kt.stop(); }
     stage_end(ctx, ST_DIGITS);
     stage_begin(ctx, ST_SORT);
     ZK_LAUNCH(ctx, k_scan, plan.nwin, 1024, 0, ctx->bucket_cnt.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(),
               ctx->bucket_cur.as<uint32_t>(), plan.nb);
-    ZK_LAUNCH(ctx, k_digits<1>, grid_for(n, 256), 256, 0, plain, n, plan, ctx->bucket_cur.as<uint32_t>(), ctx->sort_idx.as<uint32_t>());
+    { KTimed kt(ctx, KC_SORT, n);
+      ZK_LAUNCH(ctx, k_digits<1>, grid_for(n, 256), 256, 0, plain, n, plan, ctx->bucket_cur.as<uint32_t>(), ctx->sort_idx.as<uint32_t>());
+      kt.stop(); }
+    // heavy-bucket plan (device side, no host round trip): thresholds well above the uniform-case bucket size
+    {
+        const uint64_t avg = n / plan.nb + 1, total = (uint64_t)plan.nwin * n;
+        out->heavy_t = (uint32_t)(16 * avg > HEAVY_CHUNK ? (16 * avg < 0xFFFFFFFFull ? 16 * avg : 0xFFFFFFFFull) : HEAVY_CHUNK);
+        out->max_bkts = (uint32_t)(total / out->heavy_t + 1);
+        out->max_blks = (uint32_t)(total / HEAVY_CHUNK + out->max_bkts);
+        const size_t b_blk = (size_t)out->max_blks * sizeof(HeavyBlk), b_bkt = (size_t)out->max_bkts * sizeof(HeavyBkt);
+        ZK_TRY(ctx->heavy.reserve(256 + b_blk + b_bkt));
+        uint8_t *base = ctx->heavy.as<uint8_t>();
+        ZK_CUDA(cudaMemsetAsync(base, 0, 8, ctx->stream));
+        out->counters = (const uint32_t *)base; out->blks = (const HeavyBlk *)(base + 256); out->bkts = (const HeavyBkt *)(base + 256 + b_blk);
+        ZK_LAUNCH(ctx, k_heavy_plan, grid_for(slots, 256), 256, 0, ctx->bucket_cnt.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), slots, out->heavy_t,
+                  (HeavyBlk *)out->blks, (HeavyBkt *)out->bkts, (uint32_t *)base);
+    }
     stage_end(ctx, ST_SORT);
     out->plan = plan; out->n = n;
     out->idx = ctx->sort_idx.as<uint32_t>(); out->off = ctx->bucket_off.as<uint32_t>(); out->cnt = ctx->bucket_cnt.as<uint32_t>();
@@ -177,8 +258,17 @@ static int32_t msm_accumulate(zkpor_ctx *ctx, const void *d_points, const MsmSor
     const size_t slots = (size_t)plan.nwin * plan.nb;
     ZK_TRY(ctx->buckets.reserve(slots * sizeof(XYZZ<F>)));
     stage_begin(ctx, ST_ACCUM);
-    ZK_LAUNCH(ctx, (k_accumulate<F>), grid_for(slots, 128), 128, 0, (const Affine<F> *)d_points, s.idx, s.off, s.cnt, s.n, plan,
-              ctx->buckets.as<XYZZ<F>>());
+    {
+        KTimed kt(ctx, sizeof(F) == sizeof(Fp) ? KC_ACCUM_G1 : KC_ACCUM_G2, s.n);
+        ZK_LAUNCH(ctx, (k_accumulate<F>), grid_for(slots, 128), 128, 0, (const Affine<F> *)d_points, s.idx, s.off, s.cnt, s.n, plan, s.heavy_t,
+                  ctx->buckets.as<XYZZ<F>>());
+        ZK_TRY(ctx->heavy_part.reserve((size_t)s.max_blks * sizeof(XYZZ<F>)));
+        ZK_LAUNCH(ctx, (k_accumulate_heavy<F>), s.max_blks, 128, 0, (const Affine<F> *)d_points, s.idx, s.blks, s.counters, s.n, plan,
+                  ctx->heavy_part.as<XYZZ<F>>());
+        ZK_LAUNCH(ctx, (k_heavy_combine<F>), grid_for(s.max_bkts, 128), 128, 0, (const XYZZ<F> *)ctx->heavy_part.p, s.bkts, s.counters,
+                  ctx->buckets.as<XYZZ<F>>());
+        kt.stop();
+    }
     stage_end(ctx, ST_ACCUM);
     stage_begin(ctx, ST_REDUCE);
     const uint32_t L = plan.nb >= 32 ? 32 : plan.nb;

@@ -125,6 +125,10 @@ __global__ void k_scale_const(Fr *__restrict__ data, Fr f, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) st_fr(data + i, Fr::mul(ld_fr(data + i), f));
 }
+__global__ void k_mul_vec(const Fr *__restrict__ a, const Fr *__restrict__ b, Fr *__restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_fr(out + i, Fr::mul(ld_fr(a + i), ld_fr(b + i)));
+}
 // a = a*b - c
 __global__ void k_ab_minus_c(Fr *__restrict__ a, const Fr *__restrict__ b, const Fr *__restrict__ c, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,9 +190,11 @@ static int32_t run_dif(zkpor_ctx *ctx, Fr *d, const Fr *tw, uint32_t log_n) {
     while (level < log_n) {
         uint32_t R = log_n - level >= 3 ? 3 : log_n - level;
         size_t threads = (size_t)1 << (log_n - R);
+        KTimed kt(ctx, KC_NTT_PASS, (uint64_t)1 << log_n);
         if (R == 3) ZK_LAUNCH(ctx, k_ntt_dif<3>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
         else if (R == 2) ZK_LAUNCH(ctx, k_ntt_dif<2>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
         else ZK_LAUNCH(ctx, k_ntt_dif<1>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
+        kt.stop();
         level += R;
     }
     return ZKPOR_OK;
@@ -198,9 +204,11 @@ static int32_t run_dit(zkpor_ctx *ctx, Fr *d, const Fr *tw, uint32_t log_n) {
     while (level < log_n) {
         uint32_t R = log_n - level >= 3 ? 3 : log_n - level;
         size_t threads = (size_t)1 << (log_n - R);
+        KTimed kt(ctx, KC_NTT_PASS, (uint64_t)1 << log_n);
         if (R == 3) ZK_LAUNCH(ctx, k_ntt_dit<3>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
         else if (R == 2) ZK_LAUNCH(ctx, k_ntt_dit<2>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
         else ZK_LAUNCH(ctx, k_ntt_dit<1>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
+        kt.stop();
         level += R;
     }
     return ZKPOR_OK;
@@ -286,6 +294,15 @@ int32_t zkpor_ntt(zkpor_ctx *ctx, void *data, uint32_t log_n, int32_t inverse, i
     }
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     stages_collect(ctx);
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_fr_mul(zkpor_ctx *ctx, const void *a, const void *b, void *out, uint64_t n) {
+    ZK_REQUIRE(ctx && a && b && out, "fr_mul: null argument");
+    ZK_REQUIRE(is_device_ptr(a) && is_device_ptr(b) && is_device_ptr(out), "fr_mul: operands must be device memory");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    if (n) ZK_LAUNCH(ctx, k_mul_vec, grid_for(n, 256), 256, 0, (const Fr *)a, (const Fr *)b, (Fr *)out, (size_t)n);
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKPOR_OK;
 }
 
