@@ -161,7 +161,7 @@ def build_inputs(torch, zk, ctx, sh, kind):
     """wire vector + a, b, c = a o b on the constraint domain (a satisfying assignment's evaluation vectors)."""
     W, m = sh["W"], sh["n_constraints"]
     wires = dev_buf(torch, W * 32); a = dev_buf(torch, m * 32); b = dev_buf(torch, m * 32); c = dev_buf(torch, m * 32)
-    zk.synth_scalars(ctx, 0xB200, W, 1 if kind == "witness" else 0, wires)
+    zk.synth_scalars(ctx, 0xB200, W, 2 if kind == "witness" else 0, wires)
     zk.synth_scalars(ctx, 0xB201, m, 0, a); zk.synth_scalars(ctx, 0xB202, m, 0, b)
     ctx.fr_mul(a, b, c, m)
     return wires, a, b, c

@@ -1,0 +1,153 @@
+// C++ host-side mirror of the reference interfaces that libzkpor_b200 replaces (header-only, above the C-ABI in
+// zkpor_b200.h).  The reference is Go and there is no Go toolchain in the build image, so this is the compiled-language
+// host layer; names, argument meaning and error behaviour follow the reference:
+//
+//   merkletree.NewFixedDepthMerkleTree / Set / Build / Root / Get / GetProof / VerifyProof   src/utils/merkletree/merkletree.go:137-355
+//   poseidon.PoseidonBytes                                                                   src/utils/utils.go:748
+//   utils.PaddingAccountAssets / utils.AccountInfoToHash                                     src/utils/utils.go:147-186,744-750
+//   groth16.Prove (after the solver)                                                         src/prover/prover/prover.go:269
+//
+// Go panics / returned errors become C++ exceptions (zkpor::Error).  Nothing here computes a hash or a group operation
+// on the CPU: every call forwards to the GPU library and throws if no CUDA device is present.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "zkpor_b200.h"
+
+namespace zkpor {
+
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+inline void check(int32_t rc) { if (rc != ZKPOR_OK) throw Error(std::string("zkpor: ") + zkpor_last_error()); }
+
+using Hash = std::array<uint8_t, 32>;   // 32-byte big-endian canonical field element
+
+class Context {
+  public:
+    explicit Context(int device = 0) { check(zkpor_ctx_create(device, &h_)); }
+    ~Context() { zkpor_ctx_destroy(h_); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    zkpor_ctx *get() const { return h_; }
+  private:
+    zkpor_ctx *h_ = nullptr;
+};
+
+namespace utils {
+// src/utils/constants.go:103-106
+inline int GetAssetsCountOfUser(size_t n_assets) {
+    if (n_assets <= 50) return 50;
+    if (n_assets <= 500) return 500;
+    throw Error("the target counts is less than the length of assets");
+}
+struct AccountAsset { uint16_t Index; uint64_t Equity, Debt, Loan, Margin, PortfolioMargin; };
+// src/utils/utils.go:147-186 -- gaps are filled with the lowest unused asset indices first
+inline std::vector<uint64_t> PaddingAccountAssets(const std::vector<AccountAsset> &assets) {
+    const size_t target = (size_t)GetAssetsCountOfUser(assets.size()), fields = 6;
+    std::vector<uint64_t> flat(target * fields, 0);
+    const size_t padding = target - assets.size();
+    size_t cur_pad = 0, cur_idx = 0, index = 0;
+    for (const auto &a : assets) {
+        if (cur_pad < padding) {
+            for (size_t j = cur_idx; j < a.Index; j++) {
+                cur_pad++; flat[index * fields] = j; index++;
+                if (cur_pad >= padding) break;
+            }
+        }
+        uint64_t *f = &flat[index * fields];
+        f[0] = a.Index; f[1] = a.Equity; f[2] = a.Debt; f[3] = a.Loan; f[4] = a.Margin; f[5] = a.PortfolioMargin;
+        index++; cur_idx = (size_t)a.Index + 1;
+    }
+    for (size_t i = index; i < target; i++) flat[i * fields] = cur_idx++;
+    return flat;
+}
+// AccountInfoToHash for a batch of accounts of one tier; ids / totals are 32-byte big-endian (big.Int zero = all zero)
+inline std::vector<Hash> AccountInfoToHashBatch(Context &ctx, const std::vector<Hash> &ids, const std::vector<std::array<Hash, 3>> &totals,
+                                                const std::vector<uint64_t> &flat_assets, uint32_t tier) {
+    std::vector<Hash> out(ids.size());
+    if (flat_assets.size() != ids.size() * tier * 6 || totals.size() != ids.size()) throw Error("AccountInfoToHashBatch: size mismatch");
+    check(zkpor_account_leaves(ctx.get(), ids.data(), totals.data(), flat_assets.data(), ids.size(), tier, out.data()));
+    return out;
+}
+}  // namespace utils
+
+namespace poseidon {
+// poseidon.PoseidonBytes(input ...[]byte): every chunk is one big-endian element (shorter chunks are left-padded)
+inline Hash PoseidonBytes(Context &ctx, const std::vector<std::vector<uint8_t>> &input) {
+    std::vector<uint8_t> buf(input.size() * 32, 0);
+    for (size_t i = 0; i < input.size(); i++) {
+        if (input[i].size() > 32) throw Error("not support bytes bigger than modulus");
+        std::copy(input[i].begin(), input[i].end(), buf.begin() + 32 * i + (32 - input[i].size()));
+    }
+    Hash out;
+    check(zkpor_poseidon_hash_batch(ctx.get(), buf.data(), (uint32_t)input.size(), 1, out.data()));
+    return out;
+}
+}  // namespace poseidon
+
+namespace merkletree {
+class FixedDepthMerkleTree {
+  public:
+    // NewFixedDepthMerkleTree(depth, nilLeafHash, hasherFunc, capacity): the hasher is the GPU Poseidon
+    FixedDepthMerkleTree(Context &ctx, int depth, const Hash &nil_leaf, uint64_t capacity) : ctx_(ctx), depth_(depth), capacity_(capacity) {
+        if (depth > 32) throw Error("depth too large");
+        if (depth <= 0) throw Error("depth must be positive");
+        if (capacity > (1ull << depth)) throw Error("capacity exceeds maximum for given depth");
+        check(zkpor_tree_create(ctx.get(), (uint32_t)depth, nil_leaf.data(), capacity, &h_));
+    }
+    ~FixedDepthMerkleTree() { zkpor_tree_free(ctx_.get(), h_); }
+    FixedDepthMerkleTree(const FixedDepthMerkleTree &) = delete;
+    void Set(uint32_t key, const Hash &value) {
+        if (key >= capacity_) throw Error("key " + std::to_string(key) + " out of range for capacity " + std::to_string(capacity_));
+        check(zkpor_tree_set_range(ctx_.get(), h_, key, 1, value.data()));
+    }
+    void SetRange(uint64_t first_key, const std::vector<Hash> &values) { check(zkpor_tree_set_range(ctx_.get(), h_, first_key, values.size(), values.data())); }
+    void Build() { check(zkpor_tree_build(ctx_.get(), h_)); }
+    Hash Root() const { Hash r; check(zkpor_tree_root(ctx_.get(), h_, r.data())); return r; }
+    Hash Get(uint32_t key) const { Hash r; check(zkpor_tree_get_leaves(ctx_.get(), h_, &key, 1, r.data())); return r; }
+    std::vector<Hash> GetProof(uint32_t key) const {
+        if ((uint64_t)key >= (1ull << depth_)) throw Error("key " + std::to_string(key) + " out of range for tree depth " + std::to_string(depth_));
+        std::vector<Hash> p((size_t)depth_);
+        check(zkpor_tree_get_proofs(ctx_.get(), h_, &key, 1, p.data()));
+        return p;
+    }
+  private:
+    Context &ctx_; zkpor_tree *h_ = nullptr; int depth_; uint64_t capacity_;
+};
+// VerifyProof(root, key, proof, leaf, depth, hasherFunc)
+inline bool VerifyProof(Context &ctx, const Hash &root, uint32_t key, const std::vector<Hash> &proof, const Hash &leaf, int depth) {
+    if ((int)proof.size() != depth || (uint64_t)key >= (1ull << depth)) return false;
+    Hash node = leaf;
+    for (int i = 0; i < depth; i++) {
+        uint8_t pair[64];
+        const Hash &l = (key & (1u << i)) ? proof[i] : node, &r = (key & (1u << i)) ? node : proof[i];
+        std::copy(l.begin(), l.end(), pair); std::copy(r.begin(), r.end(), pair + 32);
+        check(zkpor_poseidon_hash_batch(ctx.get(), pair, 2, 1, node.data()));
+    }
+    return node == root;
+}
+}  // namespace merkletree
+
+namespace groth16 {
+class ProvingKey {   // groth16.ProvingKey resident in HBM
+  public:
+    ProvingKey(Context &ctx, const zkpor_pk_desc &desc) : ctx_(ctx) { check(zkpor_pk_upload(ctx.get(), &desc, &h_)); }
+    ~ProvingKey() { zkpor_pk_free(ctx_.get(), h_); }
+    ProvingKey(const ProvingKey &) = delete;
+    zkpor_pk *get() const { return h_; }
+  private:
+    Context &ctx_; zkpor_pk *h_ = nullptr;
+};
+// groth16.Prove after the solver; returns proof.WriteRawTo bytes.  r, s: 32-byte big-endian canonical.
+inline std::vector<uint8_t> Prove(Context &ctx, ProvingKey &pk, const void *wires, const void *a, const void *b, const void *c,
+                                  uint64_t n_constraints, const Hash &r, const Hash &s) {
+    std::vector<uint8_t> out(388); uint32_t n = 0;
+    check(zkpor_groth16_prove(ctx.get(), pk.get(), wires, a, b, c, n_constraints, r.data(), s.data(), out.data(), &n));
+    out.resize(n);
+    return out;
+}
+}  // namespace groth16
+
+}  // namespace zkpor

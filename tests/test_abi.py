@@ -71,3 +71,15 @@ def test_sum_partials_host_side():
     for i in range(2):
         parts2[i, :16] = pts2[i]; parts2[i, 16:20] = one; parts2[i, 24:28] = one
     assert orc.g2_unpack(zk.g2_sum_partials(parts2))[0] == bn.pt_mul(bn.G2_GEN, 12, bn.FP2)
+
+
+def test_cpp_host_mirror_compiles_links_and_guards():
+    """include/zkpor_b200.hpp (the compiled-language host layer) against the shared library."""
+    import subprocess
+    pkg = os.path.join(ROOT, "zkmerkle-proof-of-solvency_b200")
+    exe = os.path.join(pkg, "_build", "host_mirror_test")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cpp"),
+                           "-L", pkg, "-lzkpor_b200", "-Wl,-rpath," + pkg, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr

@@ -37,7 +37,7 @@ def main():
         nmax = 1 << 26
         pts = dev_buf(nmax * 64); sc = dev_buf(nmax * 32)
         t0 = time.perf_counter(); zk.synth_points_g1(ctx, 12345, 67891, nmax, pts); print("synth g1 2^26: %.2fs" % (time.perf_counter() - t0), flush=True)
-        for kind in (0, 1):
+        for kind in (0, 2):
             zk.synth_scalars(ctx, 7 + kind, nmax, kind, sc)
             for lg in (20, 22, 24, 26):
                 n = 1 << lg

@@ -459,3 +459,34 @@ class ProvingKey:
         _check(lib().zkpor_groth16_finish(_ptr(p), C.c_uint32(p.shape[0]), _ptr(pts["alpha1"]), _ptr(pts["beta1"]), _ptr(pts["delta1"]),
                                           _ptr(pts["beta2"]), _ptr(pts["delta2"]), rb, sb, C.c_int32(self.has_commitment), _ptr(out), C.byref(n)))
         return out[:n.value].tobytes()
+
+
+# ----------------------------------------------------------------------------------------------- multi-GPU host logic
+def chunk_bounds(length: int, rank: int, world: int):
+    """Point-chunk sharding of one key array: rank r owns [r*L/N, (r+1)*L/N)."""
+    return (length * rank) // world, (length * (rank + 1)) // world
+
+
+def finish_proof(partials: np.ndarray, alpha1, beta1, delta1, beta2, delta2, r: int, s: int, has_commitment: bool = True) -> bytes:
+    """zkpor_groth16_finish: combine the ranks' partial sums (after the all-gather) into proof.WriteRawTo bytes.
+    Pure host arithmetic -- needs no GPU and no context."""
+    p = np.ascontiguousarray(partials, dtype=np.uint8).reshape(-1, PROVE_PARTIAL_BYTES)
+    out = np.zeros(388, dtype=np.uint8)
+    n = C.c_uint32(0)
+    pts = [np.ascontiguousarray(x, dtype=np.uint64) for x in (alpha1, beta1, delta1, beta2, delta2)]
+    _check(lib().zkpor_groth16_finish(_ptr(p), C.c_uint32(p.shape[0]), *[_ptr(x) for x in pts], _be_arr(r), _be_arr(s),
+                                      C.c_int32(1 if has_commitment else 0), _ptr(out), C.byref(n)))
+    return out[:n.value].tobytes()
+
+
+def pack_partial(ar, bs1, krs_k, krs_z, commit, pok, bs2) -> np.ndarray:
+    """One rank's 7 partial sums in the layout of zkpor_groth16_prove_partial: six G1 XYZZ (128 B) then one G2 XYZZ
+    (256 B).  Inputs are XYZZ limb arrays (16 / 32 u64)."""
+    out = np.zeros(PROVE_PARTIAL_BYTES, dtype=np.uint8)
+    off = 0
+    for x, nbytes in ((ar, 128), (bs1, 128), (krs_k, 128), (krs_z, 128), (commit, 128), (pok, 128), (bs2, 256)):
+        b = np.ascontiguousarray(x, dtype=np.uint64).view(np.uint8)
+        assert b.size == nbytes
+        out[off:off + nbytes] = b
+        off += nbytes
+    return out

@@ -166,15 +166,22 @@ __global__ void __launch_bounds__(128) k_accumulate_heavy(const Affine<F> *__res
     if (threadIdx.x == 0) parts[b] = sh[0];
 }
 
+// one CTA per heavy bucket: strided sums of its block partials, then a shared-memory tree
 template <class F>
 __global__ void __launch_bounds__(128) k_heavy_combine(const XYZZ<F> *__restrict__ parts, const HeavyBkt *__restrict__ bkts,
                                                        const uint32_t *__restrict__ counters, XYZZ<F> *__restrict__ buckets) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= counters[1]) return;
-    const HeavyBkt bk = bkts[i];
+    __shared__ XYZZ<F> sh[128];
+    if (blockIdx.x >= counters[1]) return;
+    const HeavyBkt bk = bkts[blockIdx.x];
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = 0; k < bk.nblk; k++) acc.add(parts[bk.first_blk + k]);
-    buckets[bk.slot] = acc;
+    for (uint32_t k = threadIdx.x; k < bk.nblk; k += 128) acc.add(parts[bk.first_blk + k]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = 64; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { XYZZ<F> a = sh[threadIdx.x]; a.add(sh[threadIdx.x + s]); sh[threadIdx.x] = a; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) buckets[bk.slot] = sh[0];
 }
 
 // thread (w, seg): sum_{j in seg} (j+1) * B[w][j]  via running sums, segment length L
@@ -265,7 +272,7 @@ static int32_t msm_accumulate(zkpor_ctx *ctx, const void *d_points, const MsmSor
         ZK_TRY(ctx->heavy_part.reserve((size_t)s.max_blks * sizeof(XYZZ<F>)));
         ZK_LAUNCH(ctx, (k_accumulate_heavy<F>), s.max_blks, 128, 0, (const Affine<F> *)d_points, s.idx, s.blks, s.counters, s.n, plan,
                   ctx->heavy_part.as<XYZZ<F>>());
-        ZK_LAUNCH(ctx, (k_heavy_combine<F>), grid_for(s.max_bkts, 128), 128, 0, (const XYZZ<F> *)ctx->heavy_part.p, s.bkts, s.counters,
+        ZK_LAUNCH(ctx, (k_heavy_combine<F>), s.max_bkts, 128, 0, (const XYZZ<F> *)ctx->heavy_part.p, s.bkts, s.counters,
                   ctx->buckets.as<XYZZ<F>>());
         kt.stop();
     }

@@ -56,15 +56,16 @@ __device__ __forceinline__ bool lt_modulus(const Fr &v) {
     for (int i = 7; i >= 0; i--) { if (v.l[i] < FrParams::M(i)) return true; if (v.l[i] > FrParams::M(i)) return false; }
     return false;
 }
-// kind 0: uniform in [0, r).  kind 1: 60% zero, 15% one, 20% < 2^16, 5% uniform (witness-like).  Output is the limb
-// pattern itself (read it as Montgomery or canonical: uniform either way).
+// kind 0: uniform in [0, r).  kind 1: 60% zero, 15% one, 20% < 2^16, 5% uniform (witness-like), canonical integers.
+// kind 2: the kind-1 values in Montgomery form -- what a gnark wire vector holds.  For kind 0 the limb pattern can be
+// read as Montgomery or canonical: uniform either way.
 __global__ void k_synth_scalars(uint64_t seed, uint64_t n, int kind, Fr *__restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr v = Fr::zero();
     uint64_t base = mix64(seed ^ (i * 0xD1342543DE82EF95ull));
     bool uniform = true;
-    if (kind == 1) {
+    if (kind == 1 || kind == 2) {
         uint32_t t = (uint32_t)(base % 100);
         if (t < 60) uniform = false;
         else if (t < 75) { v.l[0] = 1; uniform = false; }
@@ -77,6 +78,7 @@ __global__ void k_synth_scalars(uint64_t seed, uint64_t n, int kind, Fr *__restr
             if (lt_modulus(v)) break;
         }
     }
+    if (kind == 2) v = Fr::to_mont(v);
     uint4 *d = reinterpret_cast<uint4 *>(out + i); const uint4 *s = reinterpret_cast<const uint4 *>(&v);
     d[0] = s[0]; d[1] = s[1];
 }
