@@ -18,9 +18,13 @@ the Pedersen commitment and its proof of knowledge), the proving key resident in
            itself cannot be built here: no Go toolchain, modules not vendored) on all host cores, on a bounded sample
            (2^20-domain batch of the same shape), scaled by the domain ratio.
 
-N > 1 (torchrun, one rank per GPU): the proving key is sharded by point chunk (every rank holds 1/N of each key array),
-each rank computes its partial sums, one NCCL all-gather of the 1 KiB partials, every rank finishes the proof.  The
-NTT is replicated (it does not shard without an all-to-all).  scaling = "strong".
+N > 1 (torchrun, one rank per GPU), two modes:
+  --mode replicas (default): proofs are independent objects (the reference scales the same way: several prover
+      processes pulling batches from one queue, README.md:126) -- every rank holds a full key and proves its own
+      batch each step; no data-path collective; value = N*K proofs / max-over-ranks time; scaling = "weak".
+  --mode sharded: ONE proof per step across the N GPUs (BASELINE config 4): the key is sharded by point chunk (every
+      rank holds 1/N of each key array), each rank computes its 7 partial sums, one NCCL all-gather of the 1 KiB
+      partials, every rank finishes the proof.  The NTT is replicated.  scaling = "strong".
 """
 import argparse
 import json
@@ -55,6 +59,9 @@ def parse():
     ap.add_argument("--log-n", type=int, default=26)
     ap.add_argument("--cpu-log-n", type=int, default=20)
     ap.add_argument("--scalars", default="uniform", choices=["uniform", "witness"])
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
+                    help="N>1: replicas = one independent proof per GPU per step (weak scaling, no data-path collective); "
+                         "sharded = ONE proof per step, key sharded by point chunk + NCCL all-gather of partials (strong scaling)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -185,7 +192,7 @@ def cpu_prover_sample(torch, zk, ctx, log_n, kind, threads=0):
     keep_k[sh["committed"].astype(np.int64)] = False; keep_k[sh["commitment_index"]] = False
     wa, wb, wk, cm = w[sh["inf_a"] == 0], w[sh["inf_b"] == 0], w[keep_k], w[sh["committed"].astype(np.int64)]
     ha, hb, hc = host(a).reshape(-1, 4), host(b).reshape(-1, 4), host(c).reshape(-1, 4)
-    nthreads = threads or orc.lib().orc_num_threads()
+    nthreads = threads or len(os.sched_getaffinity(0))   # torchrun sets OMP_NUM_THREADS=1: ask for every host core explicitly
     t0 = time.perf_counter()
     cpu_proof = orc.groth16_prove(arr, wa, wb, wk, cm, ha, hb, hc, r, s, threads=nthreads)
     dt = time.perf_counter() - t0
@@ -233,13 +240,14 @@ def main():
 
     # ---------------------------------------------------------------- native arm
     t_setup = time.perf_counter()
-    pk, arrays, counts = build_key(torch, zk, ctx, sh, rank, world)
+    sharded = world > 1 and args.mode == "sharded"
+    pk, arrays, counts = build_key(torch, zk, ctx, sh, rank, world) if sharded else build_key(torch, zk, ctx, sh)
     wires, a, b, c = build_inputs(torch, zk, ctx, sh, args.scalars)
     r, s = 0x1234567890ABCDEF1234567890ABCDEF % R, 0xFEDCBA0987654321FEDCBA0987654321 % R
     m = sh["n_constraints"]
     stream = torch.cuda.ExternalStream(ctx.stream())
 
-    if world == 1:
+    if not sharded:
         def step(w_, a_, b_, c_):
             return pk.prove(w_, a_, b_, c_, m, r, s)
     else:
@@ -299,21 +307,23 @@ def main():
     kstats = {name: ctx.kernel_stats(k) for k, name in enumerate(["accumulate_g1", "accumulate_g2", "ntt_pass", "digits_scatter"])}
     ctx.kernel_timing(False)
     clocks = sampler.stop()
-    value = args.steps / (ms / 1e3) * 3600.0
+    proofs_per_step = world if (world > 1 and not sharded) else 1
+    value = proofs_per_step * args.steps / (ms / 1e3) * 3600.0
 
     # ---- e2e: pinned host inputs through the same call
     e2e = None
     if not args.no_e2e:
         hw, ha, hb, hc = (x.cpu().pin_memory() for x in (wires, a, b, c))
         h2d = sum(x.numel() * 8 for x in (hw, ha, hb, hc))
-        if world == 1:
+        if not sharded:
             inputs = tuple(x.numpy() for x in (hw, ha, hb, hc))
         else:
             inputs = (hw, ha, hb, hc)
         step(*inputs)
         ems, ewall, eproof = run(args.steps, inputs)
         assert eproof == proof, "e2e proof differs from the device-resident proof"
-        e2e = {"value": args.steps / (ems / 1e3) * 3600.0, "unit": "proofs/hour", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(proof),
+        e2e = {"value": proofs_per_step * args.steps / (ems / 1e3) * 3600.0, "unit": "proofs/hour", "h2d_bytes_per_step": h2d * proofs_per_step,
+               "d2h_bytes_per_step": len(proof) * proofs_per_step,
                "ms_per_step": ems / args.steps}
         del hw, ha, hb, hc
 
@@ -337,9 +347,11 @@ def main():
     breakdown = {k: {"ms_per_step": v["total_ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in kstats.items()}
 
     line = {"metric": "proofs/hour", "value": value, "unit": "proofs/hour", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "u32 limbs (254-bit modular integers)", "data": "synthetic",
-            "config": {"workload": workload, "parallelism": "single GPU" if world == 1 else f"point-chunk sharded MSM x{world} + NCCL all-gather of partials, replicated NTT",
+            "config": {"workload": workload, "parallelism": "single GPU" if world == 1 else (f"point-chunk sharded MSM x{world} + NCCL all-gather of partials, replicated NTT" if sharded
+                                                                        else f"{world} independent proofs per step, one per GPU (full key per GPU), no data-path collective"),
+                       "proofs_per_step": proofs_per_step,
                        "l2": "inputs (>= 2 GB per vector, 21 GB key) are far larger than the 126 MB L2; no explicit flush needed",
                        "key": "synthetic key in HBM: points (k0 + i*d)*G per array", "timing": "CUDA events on the library stream, max over ranks",
                        "setup_s": setup_s},
@@ -347,7 +359,7 @@ def main():
             "proof_sha": __import__("hashlib").sha256(proof).hexdigest()[:16]}
     if e2e:
         line["e2e"] = e2e
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         pk.close(); del arrays
         torch.cuda.empty_cache()
         dt, nthreads, ok = cpu_prover_sample(torch, zk, ctx, args.cpu_log_n, args.scalars)

@@ -65,11 +65,13 @@ struct DevBuf {
 struct zkpor_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D of a/b/c overlaps the wire-only MSMs of a proof
+    cudaEvent_t copy_done = nullptr;
     int sm_count = 0;
     uint64_t launches = 0;
     int poseidon_out_lane = 1;
     // scratch
-    zk::DevBuf in_points, in_scalars, sort_idx, bucket_cnt, bucket_off, bucket_cur, buckets, partials, windows, misc, ntt_a, ntt_b, ntt_c, io, heavy, heavy_part;
+    zk::DevBuf in_points, in_scalars, sort_idx, bucket_cnt, bucket_off, bucket_cur, buckets, partials, windows, misc, ntt_a, ntt_b, ntt_c, io, heavy, heavy_part, order;
     void *pinned = nullptr; size_t pinned_cap = 0;
     // poseidon constants on device (built lazily)
     void *pos_consts = nullptr;

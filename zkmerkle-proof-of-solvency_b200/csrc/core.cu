@@ -74,6 +74,8 @@ int32_t zkpor_ctx_create(int32_t device_id, zkpor_ctx **out) {
     ctx->device = device_id;
     ctx->sm_count = prop.multiProcessorCount;
     ZK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ZK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    ZK_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
     for (int i = 0; i < ST_COUNT; i++) {
         ZK_CUDA(cudaEventCreate(&ctx->ev[i][0])); ZK_CUDA(cudaEventCreate(&ctx->ev[i][1]));
         ctx->ev_used[i] = false; ctx->last_ms[i] = 0.f;
@@ -89,8 +91,9 @@ int32_t zkpor_ctx_destroy(zkpor_ctx *ctx) {
     if (!ctx) return ZKPOR_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
     zk::DevBuf *bufs[] = {&ctx->in_points, &ctx->in_scalars, &ctx->sort_idx, &ctx->bucket_cnt, &ctx->bucket_off, &ctx->bucket_cur,
-                          &ctx->buckets, &ctx->partials, &ctx->windows, &ctx->misc, &ctx->ntt_a, &ctx->ntt_b, &ctx->ntt_c, &ctx->io, &ctx->heavy, &ctx->heavy_part};
+                          &ctx->buckets, &ctx->partials, &ctx->windows, &ctx->misc, &ctx->ntt_a, &ctx->ntt_b, &ctx->ntt_c, &ctx->io, &ctx->heavy, &ctx->heavy_part, &ctx->order};
     for (auto *b : bufs) b->release();
     zk_free_poseidon(ctx); zk_free_ntt(ctx);
     for (auto &r : ctx->klog) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -98,6 +101,8 @@ int32_t zkpor_ctx_destroy(zkpor_ctx *ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < ST_COUNT; i++) { cudaEventDestroy(ctx->ev[i][0]); cudaEventDestroy(ctx->ev[i][1]); }
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->copy_done);
     delete ctx;
     return ZKPOR_OK;
 }

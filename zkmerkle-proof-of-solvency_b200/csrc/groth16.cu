@@ -164,21 +164,22 @@ int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, con
     ZK_REQUIRE(n_constraints > 0 && n_constraints <= n, "prove: n_constraints exceeds the domain");
     ZK_CUDA(cudaSetDevice(ctx->device));
     stages_reset(ctx);
-    // wires -> HBM
+    // wires -> HBM on the compute stream (every wire-only MSM needs them); a, b, c -> padded device vectors on the
+    // copy stream, so that their H2D transfer overlaps the commitment / A / B / K multi-scalar multiplications
     const void *dw;
     stage_begin(ctx, ST_H2D);
     ZK_TRY(to_device(ctx, wires, pk->n_wires * 32, pk->wires, &dw));
-    // a, b, c -> padded device vectors
+    stage_end(ctx, ST_H2D);
     const size_t bytes = n * sizeof(Fr), in_bytes = n_constraints * sizeof(Fr);
     ZK_TRY(ctx->ntt_a.reserve(bytes)); ZK_TRY(ctx->ntt_b.reserve(bytes)); ZK_TRY(ctx->ntt_c.reserve(bytes));
     const void *src[3] = {a, b, c};
     Fr *dst[3] = {ctx->ntt_a.as<Fr>(), ctx->ntt_b.as<Fr>(), ctx->ntt_c.as<Fr>()};
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));   // the previous call's use of the NTT buffers is over
     for (int k = 0; k < 3; k++) {
-        ZK_CUDA(cudaMemcpyAsync(dst[k], src[k], in_bytes, cudaMemcpyDefault, ctx->stream));
-        if (bytes > in_bytes) ZK_CUDA(cudaMemsetAsync((uint8_t *)dst[k] + in_bytes, 0, bytes - in_bytes, ctx->stream));
+        ZK_CUDA(cudaMemcpyAsync(dst[k], src[k], in_bytes, cudaMemcpyDefault, ctx->copy_stream));
+        if (bytes > in_bytes) ZK_CUDA(cudaMemsetAsync((uint8_t *)dst[k] + in_bytes, 0, bytes - in_bytes, ctx->copy_stream));
     }
-    stage_end(ctx, ST_H2D);
-    ZK_TRY(compute_h_dev(ctx, dst[0], dst[1], dst[2], pk->log_n));
+    ZK_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
 
     uint64_t max_sub = pk->n_a; if (pk->n_b > max_sub) max_sub = pk->n_b; if (pk->n_k > max_sub) max_sub = pk->n_k; if (pk->n_ck > max_sub) max_sub = pk->n_ck;
     ZK_TRY(pk->sub.reserve((max_sub ? max_sub : 1) * 32));
@@ -207,6 +208,8 @@ int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, con
         ZK_LAUNCH(ctx, k_gather_fr, grid_for(pk->n_k, 256), 256, 0, (const Fr *)dw, (const uint32_t *)pk->idx_k, pk->n_k, sub);
         ZK_TRY(msm_g1_dev(ctx, pk->K, sub, pk->n_k, ZKPOR_SCALARS_MONT, &pp.krs_k));
     }
+    ZK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+    ZK_TRY(compute_h_dev(ctx, dst[0], dst[1], dst[2], pk->log_n));
     ZK_TRY(msm_g1_dev(ctx, pk->Z, dst[0], pk->n_z, ZKPOR_SCALARS_MONT, &pp.krs_z));
     assemble_proof(pp, pk->alpha1, pk->beta1, pk->delta1, pk->beta2, pk->delta2, r_be, s_be, pk->has_commitment, out_proof, out_len);
     stages_collect(ctx);

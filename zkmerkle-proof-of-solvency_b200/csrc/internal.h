@@ -16,7 +16,7 @@ MsmPlan msm_plan(uint64_t n);
 struct HeavyBlk { uint32_t slot, start, count; };
 struct HeavyBkt { uint32_t slot, first_blk, nblk; };
 struct MsmSorted {
-    MsmPlan plan; uint64_t n; const uint32_t *idx, *off, *cnt;
+    MsmPlan plan; uint64_t n; const uint32_t *idx, *off, *cnt, *order;   // order: slots by decreasing population
     uint32_t heavy_t, max_blks, max_bkts; const HeavyBlk *blks; const HeavyBkt *bkts; const uint32_t *counters;
 };
 

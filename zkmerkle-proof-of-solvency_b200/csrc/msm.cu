@@ -99,15 +99,26 @@ template <class F> __device__ __forceinline__ Affine<F> load_affine(const Affine
 template <class F>
 __global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict__ points, const uint32_t *__restrict__ sorted,
                                                     const uint32_t *__restrict__ off, const uint32_t *__restrict__ cnt,
-                                                    uint64_t n, MsmPlan plan, uint32_t heavy_t, XYZZ<F> *__restrict__ buckets) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)plan.nwin * plan.nb) return;
+                                                    uint64_t n, MsmPlan plan, uint32_t heavy_t, const uint32_t *__restrict__ order,
+                                                    XYZZ<F> *__restrict__ buckets) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)plan.nwin * plan.nb) return;
+    const size_t t = order[tid];
     uint32_t w = (uint32_t)(t / plan.nb);
     const uint32_t *idx = sorted + (size_t)w * n + off[t];
     uint32_t m = cnt[t];
     if (m > heavy_t) return;   // reduced by k_accumulate_heavy / k_heavy_combine
     XYZZ<F> acc = XYZZ<F>::inf();
-    if (m) {
+    if (sizeof(F) != sizeof(Fp)) {
+        // G2: the accumulator alone is 64 registers; a prefetched point would spill, so only the reference is ahead
+        uint32_t e = m ? __ldg(idx) : 0;
+        for (uint32_t k = 0; k < m; k++) {
+            uint32_t e1 = k + 1 < m ? __ldg(idx + k + 1) : 0;
+            Affine<F> p = load_affine(points + (e >> 1));
+            acc.add_affine(p, e & 1);
+            e = e1;
+        }
+    } else if (m) {
         // two-deep software pipeline: the reference for k+2 and the point for k+1 are in flight while k is added
         uint32_t e = __ldg(idx), e1 = m > 1 ? __ldg(idx + 1) : 0;
         Affine<F> p = load_affine(points + (e >> 1));
@@ -120,6 +131,39 @@ __global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict_
         }
     }
     buckets[t] = acc;
+}
+
+// ---- bucket schedule ----------------------------------------------------------------------------------------------
+// Threads of a warp run until the fullest of their 32 buckets is done (ncu, first version: 22 of 32 lanes active on
+// average).  Buckets are therefore handed to threads in order of decreasing population: a counting sort of the
+// (window, bucket) slots by their reference count, so that the 32 buckets of a warp have (almost) equal length.
+static const uint32_t SIZE_BINS = 2048;
+
+__global__ void k_size_hist(const uint32_t *__restrict__ cnt, size_t slots, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh[SIZE_BINS];
+    for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < slots; t += (size_t)gridDim.x * blockDim.x) {
+        uint32_t c = cnt[t];
+        atomicAdd(&sh[c < SIZE_BINS ? c : SIZE_BINS - 1], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// cursor[b] = number of slots in bins above b (descending order); one block of SIZE_BINS/2 threads, trivial size
+__global__ void k_size_scan(const uint32_t *__restrict__ hist, uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t sh[SIZE_BINS];
+    for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) sh[i] = hist[SIZE_BINS - 1 - i];   // reversed
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (uint32_t i = 0; i < SIZE_BINS; i++) { uint32_t v = sh[i]; sh[i] = run; run += v; } }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) cursor[SIZE_BINS - 1 - i] = sh[i];
+}
+__global__ void k_size_scatter(const uint32_t *__restrict__ cnt, size_t slots, uint32_t *__restrict__ cursor, uint32_t *__restrict__ order) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= slots) return;
+    uint32_t c = cnt[t];
+    order[atomicAdd(&cursor[c < SIZE_BINS ? c : SIZE_BINS - 1], 1u)] = (uint32_t)t;
 }
 
 // ---- heavy buckets ----------------------------------------------------------------------------------------------
@@ -253,6 +297,16 @@ int32_t msm_sort(zkpor_ctx *ctx, const void *d_scalars, uint64_t n, uint32_t fla
         ZK_LAUNCH(ctx, k_heavy_plan, grid_for(slots, 256), 256, 0, ctx->bucket_cnt.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), slots, out->heavy_t,
                   (HeavyBlk *)out->blks, (HeavyBkt *)out->bkts, (uint32_t *)base);
     }
+    // bucket schedule: slots in order of decreasing population
+    {
+        ZK_TRY(ctx->order.reserve(slots * 4 + 2 * SIZE_BINS * 4));
+        uint32_t *order = ctx->order.as<uint32_t>(), *hist = order + slots, *cursor = hist + SIZE_BINS;
+        ZK_CUDA(cudaMemsetAsync(hist, 0, SIZE_BINS * 4, ctx->stream));
+        ZK_LAUNCH(ctx, k_size_hist, 4 * ctx->sm_count, 256, 0, ctx->bucket_cnt.as<uint32_t>(), slots, hist);
+        ZK_LAUNCH(ctx, k_size_scan, 1, 256, 0, (const uint32_t *)hist, cursor);
+        ZK_LAUNCH(ctx, k_size_scatter, grid_for(slots, 256), 256, 0, ctx->bucket_cnt.as<uint32_t>(), slots, cursor, order);
+        out->order = order;
+    }
     stage_end(ctx, ST_SORT);
     out->plan = plan; out->n = n;
     out->idx = ctx->sort_idx.as<uint32_t>(); out->off = ctx->bucket_off.as<uint32_t>(); out->cnt = ctx->bucket_cnt.as<uint32_t>();
@@ -268,7 +322,7 @@ static int32_t msm_accumulate(zkpor_ctx *ctx, const void *d_points, const MsmSor
     {
         KTimed kt(ctx, sizeof(F) == sizeof(Fp) ? KC_ACCUM_G1 : KC_ACCUM_G2, s.n);
         ZK_LAUNCH(ctx, (k_accumulate<F>), grid_for(slots, 128), 128, 0, (const Affine<F> *)d_points, s.idx, s.off, s.cnt, s.n, plan, s.heavy_t,
-                  ctx->buckets.as<XYZZ<F>>());
+                  s.order, ctx->buckets.as<XYZZ<F>>());
         ZK_TRY(ctx->heavy_part.reserve((size_t)s.max_blks * sizeof(XYZZ<F>)));
         ZK_LAUNCH(ctx, (k_accumulate_heavy<F>), s.max_blks, 128, 0, (const Affine<F> *)d_points, s.idx, s.blks, s.counters, s.n, plan,
                   ctx->heavy_part.as<XYZZ<F>>());
