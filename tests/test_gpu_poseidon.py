@@ -163,3 +163,27 @@ def test_tree_argument_errors(ctx):
         t.set_range(8, np.zeros((3, 32), dtype=np.uint8), 3)
     with pytest.raises(IndexError):
         t.get_proof(16)
+
+
+def test_cex_assets_commitment_10000_elements(ctx):
+    """utils.ComputeCexAssetsCommitment (src/utils/utils.go:779-800): 500 assets x 20 packed elements through the
+    chained sponge -- 833 full-width permutations + one of width 5, twice per batch in witness.go:159-183."""
+    rng = SplitMix64(500)
+    assets = []
+    for i in range(7):
+        tiers = [(int(rng.next() % (1 << 100)), int(rng.next() % 101)) for _ in range(merkle.TIER_COUNT)]
+        assets.append(dict(total_equity=rng.next(), total_debt=rng.next(), base_price=rng.next(), loan=rng.next(), margin=rng.next(), pm=rng.next(),
+                           loan_ratios=tiers, margin_ratios=tiers[::-1], pm_ratios=tiers))
+    empty = dict(total_equity=0, total_debt=0, base_price=0, loan=0, margin=0, pm=0, loan_ratios=[(0, 0)] * 12, margin_ratios=[(0, 0)] * 12, pm_ratios=[(0, 0)] * 12)
+    elems = []
+    for a in assets + [empty] * (merkle.ASSET_COUNTS - len(assets)):
+        elems += merkle.cex_asset_packed(a)
+    assert len(elems) == 10000
+    for lane in (0, 1):
+        ctx.set_poseidon_out_lane(lane); orc.poseidon_set_out_lane(lane)
+        got = ctx.poseidon_hash_batch(orc.be32_array(elems), 10000, 1).tobytes()
+        want = orc.fr_unmont(orc.poseidon_hash(orc.fr_mont(elems)))[0].to_bytes(32, "big")
+        assert got == want
+    ctx.set_poseidon_out_lane(1); orc.poseidon_set_out_lane(1)
+    # batch commitment = PoseidonBytes(root, before, after, min, max) with the []byte{0} quirk for a zero index (witness.go:185-198)
+    assert ctx.poseidon_bytes(got, got, want, b"\x00", (1379).to_bytes(2, "big")) == ps.poseidon_bytes([got, got, want, b"\x00", (1379).to_bytes(2, "big")], 1)

@@ -47,6 +47,9 @@ def test_mont_mul_schedule(ht, which):
         fn(p(A), p(B), p(o), p(oref))
         want = a * b * rinv % mod
         assert orc.limbs_to_ints(o)[0] == want == orc.limbs_to_ints(oref)[0]
+        ok = np.zeros(4, dtype=np.uint64)
+        (ht.ht_fp_mul_kara if which == "fp" else ht.ht_fr_mul_kara)(p(A), p(B), p(ok))
+        assert orc.limbs_to_ints(ok)[0] == want, (hex(a), hex(b))
 
 
 def test_fr_add_sub_neg_inv(ht):

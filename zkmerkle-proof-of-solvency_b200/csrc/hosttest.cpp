@@ -10,6 +10,8 @@ void ht_fp_mul(const uint32_t *a, const uint32_t *b, uint32_t *o, uint32_t *oref
     Fp x, y; memcpy(&x, a, 32); memcpy(&y, b, 32);
     Fp r = Fp::mul(x, y), rr = Fp::mul_ref(x, y); memcpy(o, &r, 32); memcpy(oref, &rr, 32);
 }
+void ht_fp_mul_kara(const uint32_t *a, const uint32_t *b, uint32_t *o) { Fp x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); Fp r = Fp::mul_kara(x, y); memcpy(o, &r, 32); }
+void ht_fr_mul_kara(const uint32_t *a, const uint32_t *b, uint32_t *o) { Fr x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); Fr r = Fr::mul_kara(x, y); memcpy(o, &r, 32); }
 void ht_fr_mul(const uint32_t *a, const uint32_t *b, uint32_t *o, uint32_t *oref) {
     Fr x, y; memcpy(&x, a, 32); memcpy(&y, b, 32);
     Fr r = Fr::mul(x, y), rr = Fr::mul_ref(x, y); memcpy(o, &r, 32); memcpy(oref, &rr, 32);
