@@ -192,10 +192,20 @@ def cpu_prover_sample(torch, zk, ctx, log_n, kind, threads=0):
     keep_k[sh["committed"].astype(np.int64)] = False; keep_k[sh["commitment_index"]] = False
     wa, wb, wk, cm = w[sh["inf_a"] == 0], w[sh["inf_b"] == 0], w[keep_k], w[sh["committed"].astype(np.int64)]
     ha, hb, hc = host(a).reshape(-1, 4), host(b).reshape(-1, 4), host(c).reshape(-1, 4)
-    nthreads = threads or len(os.sched_getaffinity(0))   # torchrun sets OMP_NUM_THREADS=1: ask for every host core explicitly
-    t0 = time.perf_counter()
-    cpu_proof = orc.groth16_prove(arr, wa, wb, wk, cm, ha, hb, hc, r, s, threads=nthreads)
-    dt = time.perf_counter() - t0
+    # thread count: the fastest of {OpenMP default, all logical CPUs, half of them} -- the port must not be handicapped by
+    # SMT oversubscription or by torchrun's OMP_NUM_THREADS=1
+    ncpu = len(os.sched_getaffinity(0))
+    cands = [threads] if threads else sorted({max(1, orc.lib().orc_num_threads()), ncpu, max(1, ncpu // 2)})
+    if not threads and max(cands) == 1:
+        cands = [1]
+    best = None
+    for nt in cands:
+        t0 = time.perf_counter()
+        proof_nt = orc.groth16_prove(arr, wa, wb, wk, cm, ha, hb, hc, r, s, threads=nt)
+        dt_nt = time.perf_counter() - t0
+        if best is None or dt_nt < best[0]:
+            best = (dt_nt, nt, proof_nt)
+    dt, nthreads, cpu_proof = best
     pk.close()
     return dt, nthreads, cpu_proof == gpu_proof
 
@@ -205,6 +215,8 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference" and rank != 0:
         return 0
+    if args.impl == "reference":
+        os.environ.pop("OMP_NUM_THREADS", None)   # torchrun pins it to 1; the CPU arm uses every host core
     import torch
     import zkpor_b200 as zk
     if not torch.cuda.is_available():

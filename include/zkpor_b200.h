@@ -161,6 +161,14 @@ int32_t zkpor_tree_get_proofs(zkpor_ctx *ctx, zkpor_tree *t, const uint32_t *key
 /* device pointer of level `level` (0 = leaves) and its length in nodes, for multi-GPU subtree exchange */
 int32_t zkpor_tree_level(zkpor_ctx *ctx, zkpor_tree *t, uint32_t level, void **out_dev_ptr, uint64_t *out_len);
 
+/* ---- point decoding (pk.UnsafeReadFrom's square roots) -----------------------------------
+ * gnark-crypto bn254 encodings (ecc/bn254/marshal.go, out of tree): compressed = 32 B (G1) / 64 B (G2, X.A1 first),
+ * raw = 64 B / 128 B, big-endian, flags in the top two bits of byte 0 (00 raw, 10/11 compressed smaller/larger y,
+ * 01 infinity).  out = affine Montgomery points (host or device).  A point that is not on the curve, a coordinate
+ * >= q or a flag that contradicts `compressed` fails the call with the first offending index in the message. */
+int32_t zkpor_g1_decode_batch(zkpor_ctx *ctx, const void *in_bytes, uint64_t n, int32_t compressed, void *out_points);
+int32_t zkpor_g2_decode_batch(zkpor_ctx *ctx, const void *in_bytes, uint64_t n, int32_t compressed, void *out_points);
+
 /* ---- synthetic workloads (bench / full-size parity tooling; not on the proving path) ----------------------------
  * points[i] = (k0 + i*d) * G with known discrete logs, written as affine Montgomery points into DEVICE memory;
  * scalars = counter-based uniform Fr (kind 0) or the witness-like mix of SURVEY.md 8(d) (kind 1). */

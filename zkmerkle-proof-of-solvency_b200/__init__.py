@@ -205,6 +205,19 @@ class Context:
         _check(lib().zkpor_compute_h(self._h, _ptr(a), _ptr(b), _ptr(c), C.c_uint64(n_constraints), C.c_uint32(log_n), _ptr(out)))
         return out
 
+    # --- point decoding (pk.UnsafeReadFrom)
+    def g1_decode_batch(self, in_bytes, n: int, compressed: bool = True, out=None):
+        if out is None:
+            out = np.zeros((n, 8), dtype=np.uint64)
+        _check(lib().zkpor_g1_decode_batch(self._h, _ptr(in_bytes), C.c_uint64(n), C.c_int32(compressed), _ptr(out)))
+        return out
+
+    def g2_decode_batch(self, in_bytes, n: int, compressed: bool = True, out=None):
+        if out is None:
+            out = np.zeros((n, 16), dtype=np.uint64)
+        _check(lib().zkpor_g2_decode_batch(self._h, _ptr(in_bytes), C.c_uint64(n), C.c_int32(compressed), _ptr(out)))
+        return out
+
     # --- Poseidon
     def set_poseidon_out_lane(self, lane: int):
         _check(lib().zkpor_poseidon_set_out_lane(self._h, C.c_int32(lane)))
