@@ -153,3 +153,78 @@ class PoseidonHasher:
 def node_hash(left: bytes, right: bytes, out_lane=None) -> bytes:
     """The 2-to-1 Merkle node: h.Reset(); h.Write(left); h.Write(right); h.Sum(nil)."""
     return poseidon_bytes([left, right], out_lane)
+
+
+# ----------------------------------------------------------------------------- sparse-partial-round form
+# The product evaluates the partial rounds in the equivalent "optimized Poseidon" form (Grassi et al., appendix B):
+# constants of the linear lanes are pushed forward, the dense MDS of every partial round is factored as
+# (sparse) x diag(1, M^), the diag factor commutes with the lane-0 S-box and is pushed back into the previous round,
+# leaving one dense pre-matrix P in the last full round of the first half.  This restatement exists so that the
+# derivation is checked against the textbook permutation above (tests/test_oracle_kat.py).
+def _mat_mul(A, B):
+    n, m, k = len(A), len(B[0]), len(B)
+    return [[sum(A[i][x] * B[x][j] for x in range(k)) % R for j in range(m)] for i in range(n)]
+
+
+def _mat_inv(A):
+    n = len(A)
+    M = [list(row) + [int(i == j) for j in range(n)] for i, row in enumerate(A)]
+    for c in range(n):
+        piv = next(r for r in range(c, n) if M[r][c] % R)
+        M[c], M[piv] = M[piv], M[c]
+        inv = pow(M[c][c], -1, R)
+        M[c] = [x * inv % R for x in M[c]]
+        for r in range(n):
+            if r != c and M[r][c]:
+                f = M[r][c]
+                M[r] = [(x - f * y) % R for x, y in zip(M[r], M[c])]
+    return [row[n:] for row in M]
+
+
+@lru_cache(maxsize=None)
+def sparse_constants(t: int):
+    """(full_rc[8][t], k[R_P], P[t][t], m00, v[R_P][t-1], w[R_P][t-1]) -- see permute_sparse"""
+    rp = ROUNDS_P[t - 2]
+    rc, M = constants(t)
+    rounds = [rc[r * t:(r + 1) * t] for r in range(R_F + rp)]
+    half = R_F // 2
+    # 1. push the linear-lane constants of the partial rounds forward
+    k, carry = [], [0] * t
+    for p in range(rp):
+        cp = [(a + b) % R for a, b in zip(rounds[half + p], carry)]
+        k.append(cp[0])
+        carry = [sum(M[i][j] * cp[j] for j in range(1, t)) % R for i in range(t)]
+    full = [list(rounds[r]) for r in range(half)] + [[(a + b) % R for a, b in zip(rounds[half + rp], carry)]] + \
+           [list(rounds[r]) for r in range(half + rp + 1, R_F + rp)]
+    # 2. factor T = S_p * diag(1, T^) from the last partial round backwards
+    T = [row[:] for row in M]
+    vs, ws = [None] * rp, [None] * rp
+    for p in range(rp - 1, -1, -1):
+        That = [row[1:] for row in T[1:]]
+        inv = _mat_inv(That)
+        vs[p] = [sum(T[0][1 + x] * inv[x][j] for x in range(t - 1)) % R for j in range(t - 1)]   # v^T = T[0,1:] * T^^-1
+        ws[p] = [T[i][0] for i in range(1, t)]
+        D = [[int(i == j) if (i == 0 or j == 0) else That[i - 1][j - 1] for j in range(t)] for i in range(t)]
+        T = _mat_mul(D, M)
+    return full, k, T, M[0][0], vs, ws
+
+
+def permute_sparse(state):
+    t = len(state)
+    rp = ROUNDS_P[t - 2]
+    _, M = constants(t)
+    full, k, Pm, m00, vs, ws = sparse_constants(t)
+    s = [x % R for x in state]
+    half = R_F // 2
+    for r in range(half):
+        s = [pow((s[i] + full[r][i]) % R, 5, R) for i in range(t)]
+        mat = Pm if r == half - 1 else M
+        s = [sum(mat[i][j] * s[j] for j in range(t)) % R for i in range(t)]
+    for p in range(rp):
+        s0 = pow((s[0] + k[p]) % R, 5, R)
+        new0 = (m00 * s0 + sum(vs[p][j] * s[1 + j] for j in range(t - 1))) % R
+        s = [new0] + [(s[1 + i] + ws[p][i] * s0) % R for i in range(t - 1)]
+    for r in range(half, R_F):
+        s = [pow((s[i] + full[r][i]) % R, 5, R) for i in range(t)]
+        s = [sum(M[i][j] * s[j] for j in range(t)) % R for i in range(t)]
+    return s

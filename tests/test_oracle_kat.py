@@ -124,3 +124,13 @@ def test_padding_account_assets_rule():
     assert merkle.padding_account_assets(full)[0::6] == list(range(50))
     assert len(merkle.padding_account_assets([(i, 1, 0, 0, 0, 0) for i in range(51)])) == 3000
     assert len(merkle.pack_triples(flat)) == 100
+
+
+def test_sparse_partial_round_form_equals_textbook_permutation():
+    """the optimisation the CUDA kernels use (oracle/py/poseidon.py sparse_constants) is the same permutation"""
+    from bn254 import SplitMix64
+    rng = SplitMix64(4)
+    for t in range(2, 14):
+        st = [rng.field(R) for _ in range(t)]
+        assert ps.permute_sparse(st) == ps.permute(st)
+    assert ps.permute_sparse([0, 1, 2])[0] == 7853200120776062878684798364095072458815029376092732009249414926327459813530

@@ -19,7 +19,15 @@ namespace zk {
 static const int MAX_T = 13;
 static const int ROUNDS_P_TABLE[16] = {56, 57, 56, 60, 60, 63, 64, 63, 60, 66, 60, 65, 70, 60, 64, 68};
 
-struct PoseidonTables { const Fr *rc[MAX_T + 1]; const Fr *mds[MAX_T + 1]; int rp[MAX_T + 1]; };
+// Per width t: the 8 full-round constant vectors (`full`, 8*t), the dense MDS (`mds`), and the sparse-partial-round form
+// (Grassi et al., appendix B; derivation restated and checked in oracle/py/poseidon.py `sparse_constants`):
+//   kp[p]      lane-0 constant of partial round p (the other lanes' constants are pushed forward into full[4])
+//   pre        dense matrix P used instead of the MDS in the last full round of the first half
+//   sv[p*t+j]  row 0 of the sparse matrix of round p: sv[0] = M[0][0], sv[j] = v_j ;  sw[p*t+i] = w_i (column 0), sw[0] unused
+struct PoseidonTables {
+    const Fr *full[MAX_T + 1]; const Fr *mds[MAX_T + 1]; const Fr *pre[MAX_T + 1]; const Fr *kp[MAX_T + 1];
+    const Fr *sv[MAX_T + 1]; const Fr *sw[MAX_T + 1]; int rp[MAX_T + 1];
+};
 struct PoseidonState { PoseidonTables tab; Fr *blob = nullptr; };
 
 // ------------------------------------------------------------------------------------------------ constants (host)
@@ -69,26 +77,87 @@ static void build_constants(int t, std::vector<Fr> &rc, std::vector<Fr> &mds, in
     }
 }
 
+// (t-1)x(t-1) inverse over Fr by Gauss-Jordan (host, one-off)
+static std::vector<Fr> mat_inv(std::vector<Fr> a, int n) {
+    std::vector<Fr> inv((size_t)n * n, Fr::zero());
+    for (int i = 0; i < n; i++) inv[(size_t)i * n + i] = Fr::one();
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        while (piv < n && a[(size_t)piv * n + c].is_zero()) piv++;
+        for (int j = 0; j < n; j++) { std::swap(a[(size_t)c * n + j], a[(size_t)piv * n + j]); std::swap(inv[(size_t)c * n + j], inv[(size_t)piv * n + j]); }
+        Fr f = Fr::inv(a[(size_t)c * n + c]);
+        for (int j = 0; j < n; j++) { a[(size_t)c * n + j] = Fr::mul(a[(size_t)c * n + j], f); inv[(size_t)c * n + j] = Fr::mul(inv[(size_t)c * n + j], f); }
+        for (int r = 0; r < n; r++) {
+            if (r == c || a[(size_t)r * n + c].is_zero()) continue;
+            Fr g = a[(size_t)r * n + c];
+            for (int j = 0; j < n; j++) {
+                a[(size_t)r * n + j] = Fr::sub(a[(size_t)r * n + j], Fr::mul(g, a[(size_t)c * n + j]));
+                inv[(size_t)r * n + j] = Fr::sub(inv[(size_t)r * n + j], Fr::mul(g, inv[(size_t)c * n + j]));
+            }
+        }
+    }
+    return inv;
+}
+
+struct SparseConsts { std::vector<Fr> full, kp, pre, sv, sw; };
+
+static SparseConsts build_sparse(int t, int rp, const std::vector<Fr> &rc, const std::vector<Fr> &M) {
+    SparseConsts o;
+    auto at = [&](const std::vector<Fr> &m, int i, int j) -> const Fr & { return m[(size_t)i * t + j]; };
+    // 1. push the linear-lane constants of the partial rounds forward
+    std::vector<Fr> carry(t, Fr::zero());
+    for (int p = 0; p < rp; p++) {
+        std::vector<Fr> cp(t);
+        for (int i = 0; i < t; i++) cp[i] = Fr::add(rc[(size_t)(4 + p) * t + i], carry[i]);
+        o.kp.push_back(cp[0]);
+        for (int i = 0; i < t; i++) { Fr acc = Fr::zero(); for (int j = 1; j < t; j++) acc = Fr::add(acc, Fr::mul(at(M, i, j), cp[j])); carry[i] = acc; }
+    }
+    for (int r = 0; r < 4; r++) for (int i = 0; i < t; i++) o.full.push_back(rc[(size_t)r * t + i]);
+    for (int i = 0; i < t; i++) o.full.push_back(Fr::add(rc[(size_t)(4 + rp) * t + i], carry[i]));
+    for (int r = 5 + rp; r < 8 + rp; r++) for (int i = 0; i < t; i++) o.full.push_back(rc[(size_t)r * t + i]);
+    // 2. T = S_p * diag(1, T^), from the last partial round backwards; T <- diag(1, T^) * M
+    std::vector<Fr> T = M;
+    o.sv.assign((size_t)rp * t, Fr::zero()); o.sw.assign((size_t)rp * t, Fr::zero());
+    const int n = t - 1;
+    for (int p = rp - 1; p >= 0; p--) {
+        std::vector<Fr> That((size_t)n * n);
+        for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) That[(size_t)i * n + j] = at(T, i + 1, j + 1);
+        std::vector<Fr> inv = mat_inv(That, n);
+        o.sv[(size_t)p * t] = at(M, 0, 0);
+        for (int j = 0; j < n; j++) { Fr acc = Fr::zero(); for (int x = 0; x < n; x++) acc = Fr::add(acc, Fr::mul(at(T, 0, 1 + x), inv[(size_t)x * n + j])); o.sv[(size_t)p * t + 1 + j] = acc; }
+        for (int i = 0; i < n; i++) o.sw[(size_t)p * t + 1 + i] = at(T, i + 1, 0);
+        std::vector<Fr> nt((size_t)t * t);
+        for (int j = 0; j < t; j++) nt[j] = at(M, 0, j);                                   // row 0 of D*M = row 0 of M
+        for (int i = 1; i < t; i++) for (int j = 0; j < t; j++) { Fr acc = Fr::zero(); for (int x = 1; x < t; x++) acc = Fr::add(acc, Fr::mul(That[(size_t)(i - 1) * n + (x - 1)], at(M, x, j))); nt[(size_t)i * t + j] = acc; }
+        T = nt;
+    }
+    o.pre = T;
+    return o;
+}
+
 static int32_t get_tables(zkpor_ctx *ctx, PoseidonTables *out) {
     if (!ctx->pos_consts) {
         PoseidonState *st = new PoseidonState();
         std::vector<Fr> all;
-        size_t rc_off[MAX_T + 1] = {0}, mds_off[MAX_T + 1] = {0};
+        size_t off[MAX_T + 1][6] = {{0}};
         for (int t = 2; t <= MAX_T; t++) {
             std::vector<Fr> rc, mds; int rp;
             build_constants(t, rc, mds, rp);
+            SparseConsts sc = build_sparse(t, rp, rc, mds);
             st->tab.rp[t] = rp;
-            rc_off[t] = all.size(); all.insert(all.end(), rc.begin(), rc.end());
-            mds_off[t] = all.size(); all.insert(all.end(), mds.begin(), mds.end());
+            const std::vector<Fr> *parts[6] = {&sc.full, &mds, &sc.pre, &sc.kp, &sc.sv, &sc.sw};
+            for (int k = 0; k < 6; k++) { off[t][k] = all.size(); all.insert(all.end(), parts[k]->begin(), parts[k]->end()); }
         }
         cudaError_t e = cudaMalloc((void **)&st->blob, all.size() * sizeof(Fr));
         if (e != cudaSuccess) { delete st; set_error("cudaMalloc poseidon tables: %s", cudaGetErrorString(e)); return ZKPOR_ERR_OOM; }
         e = cudaMemcpy(st->blob, all.data(), all.size() * sizeof(Fr), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { cudaFree(st->blob); delete st; set_error("poseidon tables upload: %s", cudaGetErrorString(e)); return ZKPOR_ERR_CUDA; }
         for (int t = 0; t <= MAX_T; t++) {
-            st->tab.rc[t] = t >= 2 ? st->blob + rc_off[t] : nullptr;
-            st->tab.mds[t] = t >= 2 ? st->blob + mds_off[t] : nullptr;
-            if (t < 2) st->tab.rp[t] = 0;
+            const bool on = t >= 2;
+            st->tab.full[t] = on ? st->blob + off[t][0] : nullptr; st->tab.mds[t] = on ? st->blob + off[t][1] : nullptr;
+            st->tab.pre[t] = on ? st->blob + off[t][2] : nullptr; st->tab.kp[t] = on ? st->blob + off[t][3] : nullptr;
+            st->tab.sv[t] = on ? st->blob + off[t][4] : nullptr; st->tab.sw[t] = on ? st->blob + off[t][5] : nullptr;
+            if (!on) st->tab.rp[t] = 0;
         }
         ctx->pos_consts = st;
     }
@@ -114,16 +183,27 @@ __device__ __forceinline__ void store_be_plain(uint8_t *p, const Fr &mont) {
     for (int i = 0; i < 8; i++) w[7 - i] = __byte_perm(v.l[i], 0, 0x0123);
 }
 
-// t = 3 permutation, whole state in registers
-__device__ __forceinline__ void permute3(Fr &s0, Fr &s1, Fr &s2, const Fr *__restrict__ rc, const Fr *__restrict__ mds, int rp) {
-    Fr m[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) m[k] = mds[k];
-    const int rounds = 8 + rp;
-    for (int r = 0; r < rounds; r++) {
-        s0 = Fr::add(s0, rc[3 * r]); s1 = Fr::add(s1, rc[3 * r + 1]); s2 = Fr::add(s2, rc[3 * r + 2]);
-        s0 = sbox5(s0);
-        if (r < 4 || r >= 4 + rp) { s1 = sbox5(s1); s2 = sbox5(s2); }
+// t = 3 permutation, whole state in registers; partial rounds in the sparse form (8 products instead of 12)
+__device__ __forceinline__ void permute3(Fr &s0, Fr &s1, Fr &s2, const PoseidonTables &tab) {
+    const Fr *__restrict__ full = tab.full[3];
+    const Fr *__restrict__ kp = tab.kp[3];
+    const Fr *__restrict__ sv = tab.sv[3];
+    const Fr *__restrict__ sw = tab.sw[3];
+    const int rp = tab.rp[3];
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+        if (r == 4) {
+#pragma unroll 1
+            for (int p = 0; p < rp; p++) {
+                s0 = sbox5(Fr::add(s0, kp[p]));
+                Fr n0 = Fr::add(Fr::add(Fr::mul(sv[3 * p], s0), Fr::mul(sv[3 * p + 1], s1)), Fr::mul(sv[3 * p + 2], s2));
+                s1 = Fr::add(s1, Fr::mul(sw[3 * p + 1], s0));
+                s2 = Fr::add(s2, Fr::mul(sw[3 * p + 2], s0));
+                s0 = n0;
+            }
+        }
+        const Fr *__restrict__ m = (r == 3) ? tab.pre[3] : tab.mds[3];
+        s0 = sbox5(Fr::add(s0, full[3 * r])); s1 = sbox5(Fr::add(s1, full[3 * r + 1])); s2 = sbox5(Fr::add(s2, full[3 * r + 2]));
         Fr n0 = Fr::add(Fr::add(Fr::mul(m[0], s0), Fr::mul(m[1], s1)), Fr::mul(m[2], s2));
         Fr n1 = Fr::add(Fr::add(Fr::mul(m[3], s0), Fr::mul(m[4], s1)), Fr::mul(m[5], s2));
         Fr n2 = Fr::add(Fr::add(Fr::mul(m[6], s0), Fr::mul(m[7], s1)), Fr::mul(m[8], s2));
@@ -138,15 +218,36 @@ __device__ __forceinline__ Fr shfl_fr(const Fr &v, int src) {
     return r;
 }
 
+__device__ __forceinline__ Fr shfl_down_fr(const Fr &v, int delta) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], delta, 16);
+    return r;
+}
+
 // Width-t permutation spread over a 16-lane group: lane i owns state[i] (lanes >= t carry garbage, never read).
+// Full rounds: ARK, x^5, dense row-times-vector through shuffles.  Partial rounds (sparse form): lane 0 does the
+// S-box, every lane one product for the row-0 dot product (4-step shuffle tree) and one for its own update.
 __device__ __forceinline__ Fr group_permute(Fr s, int t, int lane, const PoseidonTables &tab) {
-    const Fr *__restrict__ rc = tab.rc[t];
-    const Fr *__restrict__ row = tab.mds[t] + (lane < t ? lane : 0) * t;
-    const int rp = tab.rp[t], rounds = 8 + rp;
-    const int li = lane < t ? lane : 0;
-    for (int r = 0; r < rounds; r++) {
-        s = Fr::add(s, rc[r * t + li]);
-        if (r < 4 || r >= 4 + rp || lane == 0) s = sbox5(s);
+    const int li = lane < t ? lane : 0, rp = tab.rp[t];
+    const Fr *__restrict__ full = tab.full[t];
+    const Fr *__restrict__ kp = tab.kp[t];
+    const Fr *__restrict__ sv = tab.sv[t];
+    const Fr *__restrict__ sw = tab.sw[t];
+    for (int r = 0; r < 8; r++) {
+        if (r == 4) {
+            for (int p = 0; p < rp; p++) {
+                if (lane == 0) s = sbox5(Fr::add(s, kp[p]));
+                Fr s0 = shfl_fr(s, 0);
+                Fr prod = lane < t ? Fr::mul(sv[p * t + li], s) : Fr::zero();
+#pragma unroll
+                for (int d = 8; d > 0; d >>= 1) prod = Fr::add(prod, shfl_down_fr(prod, d));
+                if (lane == 0) s = prod;
+                else if (lane < t) s = Fr::add(s, Fr::mul(sw[p * t + li], s0));
+            }
+        }
+        const Fr *__restrict__ row = ((r == 3) ? tab.pre[t] : tab.mds[t]) + li * t;
+        s = sbox5(Fr::add(s, full[r * t + li]));
         Fr acc = Fr::zero();
         for (int j = 0; j < t; j++) acc = Fr::add(acc, Fr::mul(row[j], shfl_fr(s, j)));
         s = acc;
@@ -228,7 +329,7 @@ __global__ void __launch_bounds__(128) k_merkle_level(const uint8_t *__restrict_
         return;
     }
     Fr s0 = Fr::zero(), s1 = load_be_mont(dl ? prev + 32 * lc : nil_prev), s2 = load_be_mont(dr ? prev + 32 * rc_ : nil_prev);
-    permute3(s0, s1, s2, tab.rc[3], tab.mds[3], tab.rp[3]);
+    permute3(s0, s1, s2, tab);
     store_be_plain(cur + 32 * p, out_lane == 0 ? s0 : out_lane == 1 ? s1 : s2);
     cur_dirty[p] = 1;
 }
@@ -238,7 +339,7 @@ __global__ void k_node_pairs(const uint8_t *__restrict__ in, uint64_t count, uin
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     Fr s0 = Fr::zero(), s1 = load_be_mont(in + 64 * i), s2 = load_be_mont(in + 64 * i + 32);
-    permute3(s0, s1, s2, tab.rc[3], tab.mds[3], tab.rp[3]);
+    permute3(s0, s1, s2, tab);
     store_be_plain(out + 32 * i, out_lane == 0 ? s0 : out_lane == 1 ? s1 : s2);
 }
 
@@ -247,7 +348,7 @@ __global__ void k_nil_chain(uint8_t *nil, uint32_t depth, PoseidonTables tab, in
     if (threadIdx.x || blockIdx.x) return;
     for (uint32_t l = 1; l <= depth; l++) {
         Fr s0 = Fr::zero(), s1 = load_be_mont(nil + 32 * (l - 1)), s2 = s1;
-        permute3(s0, s1, s2, tab.rc[3], tab.mds[3], tab.rp[3]);
+        permute3(s0, s1, s2, tab);
         store_be_plain(nil + 32 * l, out_lane == 0 ? s0 : out_lane == 1 ? s1 : s2);
     }
 }
