@@ -57,7 +57,7 @@ __device__ __forceinline__ void st_fr(Fr *p, const Fr &v) {
 
 // R levels of decimation-in-frequency starting at level `level` (level 0 has half-size n/2)
 template <int R>
-__global__ void __launch_bounds__(256) k_ntt_dif(Fr *__restrict__ data, const Fr *__restrict__ tw, uint32_t log_n, uint32_t level) {
+__global__ void __launch_bounds__(128, 4) k_ntt_dif(Fr *__restrict__ data, const Fr *__restrict__ tw, uint32_t log_n, uint32_t level) {
     const uint32_t log_h = log_n - 1 - level, log_q = log_h - (R - 1);
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ((size_t)1 << (log_n - R))) return;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) k_ntt_dif(Fr *__restrict__ data, const Fr
 
 // R levels of decimation-in-time starting at level `level` (level 0 has half-size 1)
 template <int R>
-__global__ void __launch_bounds__(256) k_ntt_dit(Fr *__restrict__ data, const Fr *__restrict__ tw, uint32_t log_n, uint32_t level) {
+__global__ void __launch_bounds__(128, 4) k_ntt_dit(Fr *__restrict__ data, const Fr *__restrict__ tw, uint32_t log_n, uint32_t level) {
     const uint32_t log_q = level;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ((size_t)1 << (log_n - R))) return;
@@ -191,9 +191,9 @@ static int32_t run_dif(zkpor_ctx *ctx, Fr *d, const Fr *tw, uint32_t log_n) {
         uint32_t R = log_n - level >= 3 ? 3 : log_n - level;
         size_t threads = (size_t)1 << (log_n - R);
         KTimed kt(ctx, KC_NTT_PASS, (uint64_t)1 << log_n);
-        if (R == 3) ZK_LAUNCH(ctx, k_ntt_dif<3>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
-        else if (R == 2) ZK_LAUNCH(ctx, k_ntt_dif<2>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
-        else ZK_LAUNCH(ctx, k_ntt_dif<1>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
+        if (R == 3) ZK_LAUNCH(ctx, k_ntt_dif<3>, grid_for(threads, 128), 128, 0, d, tw, log_n, level);
+        else if (R == 2) ZK_LAUNCH(ctx, k_ntt_dif<2>, grid_for(threads, 128), 128, 0, d, tw, log_n, level);
+        else ZK_LAUNCH(ctx, k_ntt_dif<1>, grid_for(threads, 128), 128, 0, d, tw, log_n, level);
         kt.stop();
         level += R;
     }
@@ -205,9 +205,9 @@ static int32_t run_dit(zkpor_ctx *ctx, Fr *d, const Fr *tw, uint32_t log_n) {
         uint32_t R = log_n - level >= 3 ? 3 : log_n - level;
         size_t threads = (size_t)1 << (log_n - R);
         KTimed kt(ctx, KC_NTT_PASS, (uint64_t)1 << log_n);
-        if (R == 3) ZK_LAUNCH(ctx, k_ntt_dit<3>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
-        else if (R == 2) ZK_LAUNCH(ctx, k_ntt_dit<2>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
-        else ZK_LAUNCH(ctx, k_ntt_dit<1>, grid_for(threads, 256), 256, 0, d, tw, log_n, level);
+        if (R == 3) ZK_LAUNCH(ctx, k_ntt_dit<3>, grid_for(threads, 128), 128, 0, d, tw, log_n, level);
+        else if (R == 2) ZK_LAUNCH(ctx, k_ntt_dit<2>, grid_for(threads, 128), 128, 0, d, tw, log_n, level);
+        else ZK_LAUNCH(ctx, k_ntt_dit<1>, grid_for(threads, 128), 128, 0, d, tw, log_n, level);
         kt.stop();
         level += R;
     }
