@@ -312,6 +312,114 @@ __global__ void __launch_bounds__(128) k_account_leaves(const uint8_t *__restric
     if (live && lane == 0) store_be_plain(out + g * 32, h);
 }
 
+// ---- thread-per-account leaf hashing ---------------------------------------------------------------------------------
+// One thread owns one account; its width-13 sponge state lives in shared memory (element-major, so consecutive threads
+// touch consecutive 16-byte words: conflict-free), lane 0 stays in registers through the partial rounds.  Compared
+// with the 16-lane layout every lane is busy in the partial rounds (one S-box per state instead of one per 16 lanes):
+// ~3.5 K field products per width-13 permutation instead of ~7.2 K lane-products.
+static const int TPA_THREADS = 64;
+
+struct TpaState {
+    uint4 (*p)[TPA_THREADS];
+    int tid;
+    __device__ __forceinline__ Fr ld(int e) const { Fr r; uint4 *d = reinterpret_cast<uint4 *>(&r); d[0] = p[2 * e][tid]; d[1] = p[2 * e + 1][tid]; return r; }
+    __device__ __forceinline__ void st(int e, const Fr &v) const { const uint4 *s = reinterpret_cast<const uint4 *>(&v); p[2 * e][tid] = s[0]; p[2 * e + 1][tid] = s[1]; }
+};
+
+template <int T>
+__device__ __forceinline__ void tpa_permute(const TpaState &S, const PoseidonTables &tab) {
+    const Fr *__restrict__ full = tab.full[T];
+    const Fr *__restrict__ kp = tab.kp[T];
+    const Fr *__restrict__ sv = tab.sv[T];
+    const Fr *__restrict__ sw = tab.sw[T];
+    const int rp = tab.rp[T];
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+        if (r == 4) {
+            Fr s0 = S.ld(0);
+#pragma unroll 1
+            for (int p = 0; p < rp; p++) {
+                s0 = sbox5(Fr::add(s0, kp[p]));
+                Fr acc = Fr::mul(sv[p * T], s0);
+#pragma unroll 1
+                for (int j = 1; j < T; j++) {
+                    Fr sj = S.ld(j);
+                    acc = Fr::add(acc, Fr::mul(sv[p * T + j], sj));
+                    S.st(j, Fr::add(sj, Fr::mul(sw[p * T + j], s0)));
+                }
+                s0 = acc;
+            }
+            S.st(0, s0);
+        }
+        const Fr *__restrict__ m = (r == 3) ? tab.pre[T] : tab.mds[T];
+        Fr acc[T];
+#pragma unroll
+        for (int i = 0; i < T; i++) acc[i] = Fr::zero();
+#pragma unroll 1
+        for (int j = 0; j < T; j++) {
+            Fr sj = sbox5(Fr::add(S.ld(j), full[r * T + j]));
+#pragma unroll
+            for (int i = 0; i < T; i++) acc[i] = Fr::add(acc[i], Fr::mul(m[i * T + j], sj));
+        }
+#pragma unroll
+        for (int i = 0; i < T; i++) S.st(i, acc[i]);
+    }
+}
+
+__global__ void __launch_bounds__(TPA_THREADS) k_account_leaves_tpa(const uint8_t *__restrict__ ids, const uint8_t *__restrict__ totals,
+                                                                    const uint64_t *__restrict__ flat, uint64_t n, uint32_t tier,
+                                                                    uint8_t *__restrict__ out, PoseidonTables tab, int out_lane) {
+    __shared__ uint4 smem[2 * MAX_T][TPA_THREADS];
+    const uint64_t g = (uint64_t)blockIdx.x * TPA_THREADS + threadIdx.x;
+    if (g >= n) return;                      // no block-wide synchronisation below: every thread is independent
+    TpaState S{smem, (int)threadIdx.x};
+    const uint32_t nflat = tier * 6, nel = (nflat + 2) / 3;
+    const uint64_t *f = flat + g * nflat;
+    auto packed = [&](uint32_t k) {          // a*2^128 + b*2^64 + c (src/utils/utils.go:196-218)
+        Fr v = Fr::zero();
+        uint64_t a = f[3 * k], b = 3 * k + 1 < nflat ? f[3 * k + 1] : 0, c = 3 * k + 2 < nflat ? f[3 * k + 2] : 0;
+        v.l[0] = (uint32_t)c; v.l[1] = (uint32_t)(c >> 32); v.l[2] = (uint32_t)b; v.l[3] = (uint32_t)(b >> 32);
+        v.l[4] = (uint32_t)a; v.l[5] = (uint32_t)(a >> 32);
+        return Fr::to_mont(v);
+    };
+    // assets commitment: 12 elements per width-13 permutation, lane 0 chains
+    S.st(0, Fr::zero());
+    uint32_t start = 0;
+    int width = MAX_T;
+    if (nel > 12) {
+        for (uint32_t c = 0; c < nel / 12; c++) {
+            for (int j = 1; j <= 12; j++) S.st(j, packed(start + j - 1));
+            tpa_permute<13>(S, tab);
+            start += 12;
+        }
+    }
+    if (start < nel) {
+        const int rem = (int)(nel - start);
+        for (int j = 1; j <= rem; j++) S.st(j, packed(start + j - 1));
+        width = rem + 1;
+        switch (width) {     // widths the reference's tiers produce: 50 assets -> 100 = 8*12 + 4, 500 assets -> 1000 = 83*12 + 4
+            case 5: tpa_permute<5>(S, tab); break;
+            case 13: tpa_permute<13>(S, tab); break;
+            default: {       // any other tier size: sequential fallback through the generic widths
+                switch (width) {
+                    case 2: tpa_permute<2>(S, tab); break; case 3: tpa_permute<3>(S, tab); break; case 4: tpa_permute<4>(S, tab); break;
+                    case 6: tpa_permute<6>(S, tab); break; case 7: tpa_permute<7>(S, tab); break; case 8: tpa_permute<8>(S, tab); break;
+                    case 9: tpa_permute<9>(S, tab); break; case 10: tpa_permute<10>(S, tab); break; case 11: tpa_permute<11>(S, tab); break;
+                    default: tpa_permute<12>(S, tab); break;
+                }
+            }
+        }
+    }
+    const Fr commit = S.ld(out_lane < width ? out_lane : 0);
+    // leaf = Poseidon5(id, equity, debt, collateral, commitment): width 6
+    S.st(0, Fr::zero());
+    S.st(1, load_be_mont(ids + g * 32));
+    for (int k = 0; k < 3; k++) S.st(2 + k, load_be_mont(totals + g * 96 + 32 * k));
+    S.st(5, commit);
+    tpa_permute<6>(S, tab);
+    store_be_plain(out + g * 32, S.ld(out_lane < 6 ? out_lane : 0));
+}
+
 // one Merkle level: node p of `cur` from children 2p, 2p+1 of `prev`; non-dirty children read as nil_prev,
 // a node with no dirty child becomes nil_cur (what getNodeAt returns for it) and stays non-dirty.
 __global__ void __launch_bounds__(128) k_merkle_level(const uint8_t *__restrict__ prev, const uint8_t *__restrict__ prev_dirty, uint64_t prev_len,
@@ -473,8 +581,8 @@ int32_t zkpor_account_leaves(zkpor_ctx *ctx, const void *ids_be, const void *tot
     uint8_t *dout = (uint8_t *)out_be;
     if (!out_dev) { ZK_TRY(ctx->misc.reserve(n * 32)); dout = ctx->misc.as<uint8_t>(); }
     stage_begin(ctx, ST_POSEIDON);
-    ZK_LAUNCH(ctx, k_account_leaves, grid_for(n * 16, 128), 128, 0, (const uint8_t *)d_ids, (const uint8_t *)d_tot, (const uint64_t *)d_flat, n,
-              tier, dout, tab, ctx->poseidon_out_lane);
+    ZK_LAUNCH(ctx, k_account_leaves_tpa, grid_for(n, TPA_THREADS), TPA_THREADS, 0, (const uint8_t *)d_ids, (const uint8_t *)d_tot,
+              (const uint64_t *)d_flat, n, tier, dout, tab, ctx->poseidon_out_lane);
     stage_end(ctx, ST_POSEIDON);
     if (!out_dev) {
         stage_begin(ctx, ST_D2H);
