@@ -169,6 +169,22 @@ int32_t zkpor_tree_level(zkpor_ctx *ctx, zkpor_tree *t, uint32_t level, void **o
 int32_t zkpor_g1_decode_batch(zkpor_ctx *ctx, const void *in_bytes, uint64_t n, int32_t compressed, void *out_points);
 int32_t zkpor_g2_decode_batch(zkpor_ctx *ctx, const void *in_bytes, uint64_t n, int32_t compressed, void *out_points);
 
+/* ---- groth16.Setup building blocks (src/keygen/main.go:42) -------------------------------
+ * curve.BatchScalarMultiplicationG1/G2: out[i] = scalars[i] * base (affine, host or device). */
+int32_t zkpor_g1_fixed_base_batch(zkpor_ctx *ctx, const void *base_affine64, const void *scalars, uint64_t n, uint32_t flags, void *out_points);
+int32_t zkpor_g2_fixed_base_batch(zkpor_ctx *ctx, const void *base_affine128, const void *scalars, uint64_t n, uint32_t flags, void *out_points);
+/* Lagrange basis of the size-2^log_n domain at tau: out[k] = (tau^n - 1)/n * w^k/(tau - w^k)  (device, Montgomery) */
+int32_t zkpor_setup_lagrange(zkpor_ctx *ctx, const uint8_t tau_be[32], uint32_t log_n, void *out_dev);
+/* per-wire query evaluation: out[i] = sum_{e in column i} coeffs[e] * lagrange[rows[e]]; the R1CS matrix is passed in
+ * compressed-sparse-column form (col_ptr has n_wires+1 entries) -- setupABC of gnark's setup.go */
+int32_t zkpor_setup_wire_sums(zkpor_ctx *ctx, const uint64_t *col_ptr, const uint32_t *rows, const void *coeffs, uint64_t nnz,
+                              const void *lagrange_dev, uint64_t n_wires, void *out_dev);
+/* out = (ka*a + kb*b + kc*c) * k  element-wise (device vectors; scalars canonical big-endian) */
+int32_t zkpor_fr_lincomb3(zkpor_ctx *ctx, const void *a, const void *b, const void *c, const uint8_t ka_be[32], const uint8_t kb_be[32],
+                          const uint8_t kc_be[32], const uint8_t k_be[32], uint64_t n, void *out);
+/* out[i] = first * ratio^i, or first * ratio^bitrev(i, log_n) when bitrev != 0 (pk.G1.Z is stored bit-reversed) */
+int32_t zkpor_fr_powers(zkpor_ctx *ctx, const uint8_t first_be[32], const uint8_t ratio_be[32], uint64_t n, uint32_t log_n, int32_t bitrev, void *out_dev);
+
 /* ---- synthetic workloads (bench / full-size parity tooling; not on the proving path) ----------------------------
  * points[i] = (k0 + i*d) * G with known discrete logs, written as affine Montgomery points into DEVICE memory;
  * scalars = counter-based uniform Fr (kind 0) or the witness-like mix of SURVEY.md 8(d) (kind 1). */

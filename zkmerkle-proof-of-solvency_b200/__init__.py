@@ -474,6 +474,86 @@ class ProvingKey:
         return out[:n.value].tobytes()
 
 
+# ----------------------------------------------------------------------------------------------- Setup
+def g1_fixed_base_batch(ctx: Context, base, scalars, n: int, out, flags: int = ZKPOR_SCALARS_MONT):
+    """curve.BatchScalarMultiplicationG1: out[i] = scalars[i] * base"""
+    _check(lib().zkpor_g1_fixed_base_batch(ctx._h, _ptr(base), _ptr(scalars), C.c_uint64(n), C.c_uint32(flags), _ptr(out)))
+    return out
+
+
+def g2_fixed_base_batch(ctx: Context, base, scalars, n: int, out, flags: int = ZKPOR_SCALARS_MONT):
+    _check(lib().zkpor_g2_fixed_base_batch(ctx._h, _ptr(base), _ptr(scalars), C.c_uint64(n), C.c_uint32(flags), _ptr(out)))
+    return out
+
+
+def groth16_setup(ctx: Context, log_n: int, n_wires: int, nb_public: int, csc_a, csc_b, csc_c, private_committed, commitment_index: int, toxic: dict):
+    """groth16.Setup (src/keygen/main.go:42; gnark backend/groth16/bn254/setup.go) with EXPLICIT toxic waste
+    {alpha, beta, gamma, delta, tau, sigma} -- gnark draws it with crypto/rand.  csc_x = (col_ptr u64[n_wires+1],
+    rows u32[nnz], coeffs Fr-Montgomery (nnz,4) u64) for the A / B / C matrices in column (= wire) order.
+    Everything heavy runs on the GPU: Lagrange basis at tau, per-wire sums, the K / Z scalars, and the fixed-base
+    batch multiplications.  Returns (pk_kwargs for ProvingKey(...), extras) with point arrays as CUDA tensors."""
+    import torch
+    n = 1 << log_n
+    dev = lambda nb: torch.empty((nb + 7) // 8, dtype=torch.int64, device="cuda")
+    be = lambda v: _be_arr(v)
+    inv = lambda v: pow(v % R_MOD, -1, R_MOD)
+    lag = dev(n * 32)
+    _check(lib().zkpor_setup_lagrange(ctx._h, be(toxic["tau"]), C.c_uint32(log_n), _ptr(lag)))
+    sums = []
+    for col_ptr, rows, coeffs in (csc_a, csc_b, csc_c):
+        col_ptr = np.ascontiguousarray(col_ptr, dtype=np.uint64); rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64)
+        out = dev(n_wires * 32)
+        _check(lib().zkpor_setup_wire_sums(ctx._h, _ptr(col_ptr), _ptr(rows), _ptr(coeffs), C.c_uint64(rows.size), _ptr(lag), C.c_uint64(n_wires), _ptr(out)))
+        sums.append(out)
+    A, B, Cc = sums
+    k_gamma, k_delta = dev(n_wires * 32), dev(n_wires * 32)
+    for out, k in ((k_gamma, inv(toxic["gamma"])), (k_delta, inv(toxic["delta"]))):   # (beta*A + alpha*B + C) / {gamma, delta}
+        _check(lib().zkpor_fr_lincomb3(ctx._h, _ptr(A), _ptr(B), _ptr(Cc), be(toxic["beta"]), be(toxic["alpha"]), be(1), be(k), C.c_uint64(n_wires), _ptr(out)))
+    v4 = lambda t: t.view(-1, 4)
+    committed = np.asarray(private_committed, dtype=np.int64)
+    has_commit = commitment_index is not None and commitment_index >= 0
+    is_vk = np.zeros(n_wires, dtype=bool); is_vk[:nb_public] = True
+    if has_commit:
+        is_vk[commitment_index] = True
+    is_ck = np.zeros(n_wires, dtype=bool); is_ck[committed] = True
+    idx = lambda mask: torch.from_numpy(np.nonzero(mask)[0]).cuda()
+    vk_s = v4(k_gamma)[idx(is_vk)].contiguous(); ck_s = v4(k_gamma)[idx(is_ck)].contiguous(); pk_s = v4(k_delta)[idx(~is_vk & ~is_ck)].contiguous()
+    ck_sigma_s = torch.empty_like(ck_s)
+    if ck_s.shape[0]:
+        _check(lib().zkpor_fr_lincomb3(ctx._h, _ptr(ck_s), _ptr(ck_s), _ptr(ck_s), be(1), be(0), be(0), be(toxic["sigma"]), C.c_uint64(ck_s.shape[0]), _ptr(ck_sigma_s)))
+    zt = (pow(toxic["tau"], n, R_MOD) - 1) % R_MOD
+    Z = dev(n * 32)
+    _check(lib().zkpor_fr_powers(ctx._h, be(zt * inv(toxic["delta"]) % R_MOD), be(toxic["tau"]), C.c_uint64(n), C.c_uint32(log_n), C.c_int32(1), _ptr(Z)))
+    Z_s = v4(Z)[: n - 1].contiguous()
+    inf_a = (v4(A) == 0).all(dim=1); inf_b = (v4(B) == 0).all(dim=1)
+    A_s = v4(A)[~inf_a].contiguous(); B_s = v4(B)[~inf_b].contiguous()
+    g1 = dev(64); g2 = dev(128)
+    synth_points_g1(ctx, 1, 1, 1, g1); synth_points_g2(ctx, 1, 1, 1, g2)
+
+    def fb(scalars, g2_=False):
+        cnt = scalars.shape[0]
+        out = dev(max(cnt, 1) * (128 if g2_ else 64))
+        if cnt:
+            (g2_fixed_base_batch if g2_ else g1_fixed_base_batch)(ctx, g2 if g2_ else g1, scalars, cnt, out)
+        return out
+
+    def one(v, g2_=False):
+        s = torch.from_numpy(np.frombuffer(b"".join(int((v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF).to_bytes(8, "little") for k in range(4)), dtype=np.int64).copy()).cuda()
+        o = dev(128 if g2_ else 64)
+        (g2_fixed_base_batch if g2_ else g1_fixed_base_batch)(ctx, g2 if g2_ else g1, s, 1, o, ZKPOR_SCALARS_PLAIN)
+        return o.cpu().numpy().view(np.uint64).copy()
+
+    pk_kwargs = dict(log_n=log_n, A=fb(A_s), B1=fb(B_s), K=fb(pk_s), Z=fb(Z_s), B2=fb(B_s, True),
+                     alpha1=one(toxic["alpha"]), beta1=one(toxic["beta"]), delta1=one(toxic["delta"]), beta2=one(toxic["beta"], True), delta2=one(toxic["delta"], True),
+                     n_a=int(A_s.shape[0]), n_b=int(B_s.shape[0]), n_k=int(pk_s.shape[0]), n_z=n - 1,
+                     infinity_a=inf_a.cpu().numpy().astype(np.uint8), infinity_b=inf_b.cpu().numpy().astype(np.uint8), n_public=nb_public)
+    if has_commit:
+        pk_kwargs.update(ck_basis=fb(ck_s), ck_basis_exp_sigma=fb(ck_sigma_s), private_committed=committed.astype(np.uint64), commitment_index=commitment_index)
+    extras = dict(vk_K=fb(vk_s), gamma2=one(toxic["gamma"], True), n_vk=int(vk_s.shape[0]))
+    return pk_kwargs, extras
+
+
 # ----------------------------------------------------------------------------------------------- multi-GPU host logic
 def chunk_bounds(length: int, rank: int, world: int):
     """Point-chunk sharding of one key array: rank r owns [r*L/N, (r+1)*L/N)."""
