@@ -71,7 +71,9 @@ static int32_t fixed_base_batch(zkpor_ctx *ctx, const void *base_affine, const v
     ZK_CUDA(cudaSetDevice(ctx->device));
     if (n == 0) return ZKPOR_OK;
     stages_reset(ctx);
-    Affine<F> base; memcpy(&base, base_affine, sizeof base);
+    Affine<F> base;
+    if (is_device_ptr(base_affine)) ZK_CUDA(cudaMemcpy(&base, base_affine, sizeof base, cudaMemcpyDeviceToHost));
+    else memcpy(&base, base_affine, sizeof base);
     const void *ds;
     stage_begin(ctx, ST_H2D);
     ZK_TRY(to_device(ctx, scalars, n * 32, ctx->in_scalars, &ds));
