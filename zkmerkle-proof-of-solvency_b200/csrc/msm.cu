@@ -209,23 +209,27 @@ __global__ void __launch_bounds__(128) k_accumulate_heavy(const Affine<F> *__res
                                                           const HeavyBlk *__restrict__ blks, const uint32_t *__restrict__ counters,
                                                           uint64_t n, MsmPlan plan, XYZZ<F> *__restrict__ parts) {
     __shared__ XYZZ<F> sh[128];
-    const uint32_t b = blockIdx.x;
-    if (b >= counters[0]) return;
-    const HeavyBlk blk = blks[b];
-    const uint32_t *idx = sorted + (size_t)(blk.slot / plan.nb) * n + blk.start;
-    XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = threadIdx.x; k < blk.count; k += 128) {
-        uint32_t e = __ldg(idx + k);
-        Affine<F> p = load_affine(points + (e >> 1));
-        acc.add_affine(p, e & 1);
-    }
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (uint32_t s = 64; s > 0; s >>= 1) {
-        if (threadIdx.x < s) { XYZZ<F> a = sh[threadIdx.x]; a.add(sh[threadIdx.x + s]); sh[threadIdx.x] = a; }
+    const uint32_t nblk = counters[0];
+    // persistent CTAs striding over the block descriptors: with no heavy bucket (uniform scalars) the launch is a few
+    // hundred CTAs that exit at once (a grid of max_blks ~ 4*10^5 empty CTAs cost 11 ms per MSM in the first version)
+    for (uint32_t b = blockIdx.x; b < nblk; b += gridDim.x) {
+        const HeavyBlk blk = blks[b];
+        const uint32_t *idx = sorted + (size_t)(blk.slot / plan.nb) * n + blk.start;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t k = threadIdx.x; k < blk.count; k += 128) {
+            uint32_t e = __ldg(idx + k);
+            Affine<F> p = load_affine(points + (e >> 1));
+            acc.add_affine(p, e & 1);
+        }
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (uint32_t s = 64; s > 0; s >>= 1) {
+            if (threadIdx.x < s) { XYZZ<F> a = sh[threadIdx.x]; a.add(sh[threadIdx.x + s]); sh[threadIdx.x] = a; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) parts[b] = sh[0];
         __syncthreads();
     }
-    if (threadIdx.x == 0) parts[b] = sh[0];
 }
 
 // one CTA per heavy bucket: strided sums of its block partials, then a shared-memory tree
@@ -233,17 +237,20 @@ template <class F>
 __global__ void __launch_bounds__(128) k_heavy_combine(const XYZZ<F> *__restrict__ parts, const HeavyBkt *__restrict__ bkts,
                                                        const uint32_t *__restrict__ counters, XYZZ<F> *__restrict__ buckets) {
     __shared__ XYZZ<F> sh[128];
-    if (blockIdx.x >= counters[1]) return;
-    const HeavyBkt bk = bkts[blockIdx.x];
-    XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = threadIdx.x; k < bk.nblk; k += 128) acc.add(parts[bk.first_blk + k]);
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (uint32_t s = 64; s > 0; s >>= 1) {
-        if (threadIdx.x < s) { XYZZ<F> a = sh[threadIdx.x]; a.add(sh[threadIdx.x + s]); sh[threadIdx.x] = a; }
+    const uint32_t nbkt = counters[1];
+    for (uint32_t i = blockIdx.x; i < nbkt; i += gridDim.x) {
+        const HeavyBkt bk = bkts[i];
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t k = threadIdx.x; k < bk.nblk; k += 128) acc.add(parts[bk.first_blk + k]);
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (uint32_t s = 64; s > 0; s >>= 1) {
+            if (threadIdx.x < s) { XYZZ<F> a = sh[threadIdx.x]; a.add(sh[threadIdx.x + s]); sh[threadIdx.x] = a; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) buckets[bk.slot] = sh[0];
         __syncthreads();
     }
-    if (threadIdx.x == 0) buckets[bk.slot] = sh[0];
 }
 
 // thread (w, seg): sum_{j in seg} (j+1) * B[w][j]  via running sums, segment length L
@@ -342,9 +349,9 @@ static int32_t msm_accumulate(zkpor_ctx *ctx, const void *d_points, const MsmSor
         ZK_LAUNCH(ctx, (k_accumulate<F>), grid_for(slots, 128), 128, 0, (const Affine<F> *)d_points, s.idx, s.off, s.cnt, s.n, plan, s.heavy_t,
                   s.order, ctx->buckets.as<XYZZ<F>>());
         ZK_TRY(ctx->heavy_part.reserve((size_t)s.max_blks * sizeof(XYZZ<F>)));
-        ZK_LAUNCH(ctx, (k_accumulate_heavy<F>), s.max_blks, 128, 0, (const Affine<F> *)d_points, s.idx, s.blks, s.counters, s.n, plan,
+        ZK_LAUNCH(ctx, (k_accumulate_heavy<F>), (s.max_blks < 8u * ctx->sm_count ? s.max_blks : 8u * ctx->sm_count), 128, 0, (const Affine<F> *)d_points, s.idx, s.blks, s.counters, s.n, plan,
                   ctx->heavy_part.as<XYZZ<F>>());
-        ZK_LAUNCH(ctx, (k_heavy_combine<F>), s.max_bkts, 128, 0, (const XYZZ<F> *)ctx->heavy_part.p, s.bkts, s.counters,
+        ZK_LAUNCH(ctx, (k_heavy_combine<F>), (s.max_bkts < 4u * ctx->sm_count ? s.max_bkts : 4u * ctx->sm_count), 128, 0, (const XYZZ<F> *)ctx->heavy_part.p, s.bkts, s.counters,
                   ctx->buckets.as<XYZZ<F>>());
         kt.stop();
     }
