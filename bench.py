@@ -353,7 +353,11 @@ def main():
         terms_per_launch = ks["units"] / ks["launches"]
         achieved = 96.0 * terms_per_launch / (per_launch_ms / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": "k_accumulate<Fp> (G1 bucket accumulation)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": None, "bytes_per_term": 96, "terms_per_launch": terms_per_launch,
+                "frac": achieved / peak, "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: 86.63 GB for the 49 526 340-term launch of this
+                # very workload under `ncu --set full` (profiles/r01_SUMMARY.md) = 1 749 B/term, scaled to the average launch
+                "traffic": 1749.2 * terms_per_launch, "traffic_source": "ncu --set full, bench.py at 2^26: 85.75 GB read + 0.88 GB written per 49.5 M-term launch (profiles/r01_SUMMARY.md)",
+                "bytes_per_term": 96, "terms_per_launch": terms_per_launch,
                 "launch_ms": per_launch_ms, "launches": ks["launches"], "share_of_step": ks["total_ms"] / ms,
                 "note": "integer-ALU bound: ~13 windows x 10 field mul per term; see DESIGN.md for the modmul roofline"}
     breakdown = {k: {"ms_per_step": v["total_ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in kstats.items()}
