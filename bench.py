@@ -235,8 +235,8 @@ def main():
     if args.impl == "reference":
         dt, nthreads, ok = cpu_prover_sample(torch, zk, ctx, args.cpu_log_n, args.scalars)
         times = [dt]
-        for _ in range(max(0, min(args.steps, 3) - 1)):
-            times.append(cpu_prover_sample(torch, zk, ctx, args.cpu_log_n, args.scalars)[0])
+        for _ in range(max(0, min(args.steps, 3) - 1)):      # later steps reuse the thread count the first one selected
+            times.append(cpu_prover_sample(torch, zk, ctx, args.cpu_log_n, args.scalars, threads=nthreads)[0])
         t = min(times)
         v = 3600.0 / (t * ratio)
         line = {"impl": "reference", "metric": "proofs/hour", "value": v, "unit": "proofs/hour", "n_gpus": args.gpus, "steps": len(times),
