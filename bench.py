@@ -22,9 +22,10 @@ N > 1 (torchrun, one rank per GPU), two modes:
   --mode replicas (default): proofs are independent objects (the reference scales the same way: several prover
       processes pulling batches from one queue, README.md:126) -- every rank holds a full key and proves its own
       batch each step; no data-path collective; value = N*K proofs / max-over-ranks time; scaling = "weak".
-  --mode sharded: ONE proof per step across the N GPUs (BASELINE config 4): the key is sharded by point chunk (every
-      rank holds 1/N of each key array), each rank computes its 7 partial sums, one NCCL all-gather of the 1 KiB
-      partials, every rank finishes the proof.  The NTT is replicated.  scaling = "strong".
+  --mode sharded: ONE proof per step across the N GPUs (BASELINE config 4): the key is sharded by point chunk; rank 0
+      runs computeH while the others start on the wire-side MSMs (rank 0 holds a correspondingly smaller chunk), h is
+      broadcast over NVLink, every rank adds its share of the Z MSM, one NCCL all-gather of the partial sums (2 KiB per
+      rank), every rank finishes the proof.  scaling = "strong".
 """
 import argparse
 import json
@@ -85,6 +86,20 @@ def shape_for(log_n):
                 n_constraints=min(n, int(n * SHAPE["constraints"])))
 
 
+# Sharded (one proof across N GPUs) schedule: rank 0 runs computeH while the other ranks start on the wire-side MSMs; h is
+# then broadcast over NVLink and every rank takes an even share of the Z MSM.  Per-proof kernel time at 2^26 on one B200
+# (profiles/r01_SUMMARY.md): computeH 113 ms, wire-side MSMs (A, B1, B2, K, commitment) ~750 ms, Z MSM ~140 ms.
+COST_MS = dict(ntt=113.0, msm_wires=750.0, msm_z=140.0)
+
+
+def shard_weight_rank0(world):
+    """fraction of the wire-side MSM work given to rank 0 so that all ranks finish together"""
+    if world <= 1:
+        return 1.0
+    t = (COST_MS["ntt"] + COST_MS["msm_wires"] + COST_MS["msm_z"]) / world
+    return min(1.0 / world, max(0.0, (t - COST_MS["ntt"] - COST_MS["msm_z"] / world) / COST_MS["msm_wires"]))
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -135,13 +150,23 @@ def single_point(torch, zk, ctx, k, g2=False):
 def build_key(torch, zk, ctx, sh, rank=0, world=1):
     """Synthetic proving key of the zkpor50_1380 shape directly in HBM (points with known discrete logs).  With
     world > 1 this rank holds the [rank/world, (rank+1)/world) chunk of every array (point-chunk sharding)."""
-    def chunk(L):
-        return (L * rank) // world, (L * (rank + 1)) // world
+    f0 = shard_weight_rank0(world)
+
+    def chunk(L, even=False):
+        """rank 0 also runs computeH, so it takes the fraction f0 of every wire-side array (the rest is split evenly over the
+        other ranks); the Z array, consumed after h has been broadcast, is split evenly."""
+        if world == 1 or even:
+            return (L * rank) // world, (L * (rank + 1)) // world
+        cut0 = int(L * f0)
+        if rank == 0:
+            return 0, cut0
+        rest = L - cut0
+        return cut0 + (rest * (rank - 1)) // (world - 1), cut0 + (rest * rank) // (world - 1)
 
     arrays, counts = {}, {}
     for name, L, g2 in (("A", sh["n_a"], False), ("B1", sh["n_b"], False), ("K", sh["n_k"], False), ("Z", sh["n_z"], False),
                         ("B2", sh["n_b"], True), ("ck", sh["n_ck"], False), ("ck_sigma", sh["n_ck"], False)):
-        lo, hi = chunk(L)
+        lo, hi = chunk(L, even=(name == "Z"))
         key = {"B1": "B", "B2": "B", "ck": "CK", "ck_sigma": "CK"}.get(name, name)
         k0, d = SEEDS[key]
         if name == "ck_sigma":
@@ -273,18 +298,28 @@ def main():
         ia, ib, ik, ic = sl("A", ia), sl("B1", ib), sl("K", ik), sl("ck", ic)
         h = dev_buf(torch, sh["n"] * 32)
         zlo, zhi = counts["Z"]
-        gathered = torch.empty((world, zk.PROVE_PARTIAL_BYTES), dtype=torch.uint8, device="cuda")
+        gathered = torch.empty((world, 2, zk.PROVE_PARTIAL_BYTES), dtype=torch.uint8, device="cuda")
 
         def step(w_, a_, b_, c_):
-            if not w_.is_cuda:    # e2e: this rank's H2D copies are part of the step
-                w_, a_, b_, c_ = w_.cuda(non_blocking=True), a_.cuda(non_blocking=True), b_.cuda(non_blocking=True), c_.cuda(non_blocking=True)
+            if not w_.is_cuda:    # e2e: this rank's H2D copies are part of the step (a, b, c are only needed by the computeH rank)
+                w_ = w_.cuda(non_blocking=True)
+                if rank == 0:
+                    a_, b_, c_ = a_.cuda(non_blocking=True), b_.cuda(non_blocking=True), c_.cuda(non_blocking=True)
             wv = w_.view(-1, 4)
             wa, wb, wk, cm = wv[ia].contiguous(), wv[ib].contiguous(), wv[ik].contiguous(), wv[ic].contiguous()
             torch.cuda.synchronize()
-            ctx.compute_h(a_, b_, c_, m, sh["log_n"], out=h)
-            part = pk.prove_partial(wa, wb, wk, cm, h.view(-1, 4)[zlo:zhi].contiguous(), zhi - zlo)
-            dist.all_gather_into_tensor(gathered, torch.from_numpy(part).cuda())
-            return pk.finish(gathered.cpu().numpy(), r, s)
+            if rank == 0:
+                ctx.compute_h(a_, b_, c_, m, sh["log_n"], out=h)
+            else:
+                part_w = pk.prove_partial(wa, wb, wk, cm, None, 0)
+            dist.broadcast(h, src=0)                      # 2 GiB over NVLink
+            torch.cuda.synchronize()
+            if rank == 0:
+                part_w = pk.prove_partial(wa, wb, wk, cm, None, 0)
+            part_z = pk.prove_partial(None, None, None, None, h.view(-1, 4)[zlo:zhi], zhi - zlo)
+            mine = torch.from_numpy(np.stack([part_w, part_z])).cuda()
+            dist.all_gather_into_tensor(gathered, mine)
+            return pk.finish(gathered.cpu().numpy().reshape(-1, zk.PROVE_PARTIAL_BYTES), r, s)
 
     def barrier():
         torch.cuda.synchronize()
@@ -365,7 +400,7 @@ def main():
     line = {"metric": "proofs/hour", "value": value, "unit": "proofs/hour", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "u32 limbs (254-bit modular integers)", "data": "synthetic",
-            "config": {"workload": workload, "parallelism": "single GPU" if world == 1 else (f"point-chunk sharded MSM x{world} + NCCL all-gather of partials, replicated NTT" if sharded
+            "config": {"workload": workload, "parallelism": "single GPU" if world == 1 else (f"point-chunk sharded MSM x{world} (rank 0 also runs computeH and broadcasts h over NVLink) + NCCL all-gather of the 2 KiB partials" if sharded
                                                                         else f"{world} independent proofs per step, one per GPU (full key per GPU), no data-path collective"),
                        "proofs_per_step": proofs_per_step,
                        "l2": "inputs (>= 2 GB per vector, 21 GB key) are far larger than the 126 MB L2; no explicit flush needed",
