@@ -310,12 +310,9 @@ def main():
             torch.cuda.synchronize()
             if rank == 0:
                 ctx.compute_h(a_, b_, c_, m, sh["log_n"], out=h)
-            else:
-                part_w = pk.prove_partial(wa, wb, wk, cm, None, 0)
-            dist.broadcast(h, src=0)                      # 2 GiB over NVLink
+            part_w = pk.prove_partial(wa, wb, wk, cm, None, 0)   # rank 0's chunk is smaller by the time computeH takes
+            dist.broadcast(h, src=0)                              # 2 GiB over NVLink, all ranks arrive together
             torch.cuda.synchronize()
-            if rank == 0:
-                part_w = pk.prove_partial(wa, wb, wk, cm, None, 0)
             part_z = pk.prove_partial(None, None, None, None, h.view(-1, 4)[zlo:zhi], zhi - zlo)
             mine = torch.from_numpy(np.stack([part_w, part_z])).cuda()
             dist.all_gather_into_tensor(gathered, mine)
