@@ -73,6 +73,12 @@ int32_t zkpor_msm_g2(zkpor_ctx *ctx, const void *points /* n x 128 B */, const v
  * 256 B for G2) so that ranks can exchange partials (one NCCL all-gather) and finish with zkpor_g{1,2}_sum_partials. */
 int32_t zkpor_msm_g1_partial(zkpor_ctx *ctx, const void *points, const void *scalars, uint64_t n, uint32_t flags, void *out_xyzz128);
 int32_t zkpor_msm_g2_partial(zkpor_ctx *ctx, const void *points, const void *scalars, uint64_t n, uint32_t flags, void *out_xyzz256);
+/* Bucket accumulation strategy.  Default (0): every bucket is summed in extended-Jacobian form.  -1 / k > 0: a bucket is
+ * first summed as a binary tree of batched affine additions (one shared inversion per batch of 64) for an automatic number
+ * of levels / at most k levels.  Results are identical for every setting (an MSM result is a group element); on B200 the
+ * affine rounds measured no faster than the default, so the knob exists for measurement and for the parity
+ * tests.  Environment override at context creation: ZKPOR_AFFINE_ROUNDS. */
+int32_t zkpor_msm_set_affine_rounds(zkpor_ctx *ctx, int32_t rounds);
 int32_t zkpor_g1_sum_partials(const void *partials_xyzz /* host, k x 128 B */, uint32_t k, void *out_affine64);
 int32_t zkpor_g2_sum_partials(const void *partials_xyzz /* host, k x 256 B */, uint32_t k, void *out_affine128);
 
@@ -133,6 +139,41 @@ int32_t zkpor_groth16_finish(const void *partials /* k x ZKPOR_PROVE_PARTIAL_BYT
                              const void *g1_beta, const void *g1_delta, const void *g2_beta, const void *g2_delta,
                              const uint8_t r_be[32], const uint8_t s_be[32], int32_t has_commitment, uint8_t *out_proof,
                              uint32_t *out_len);
+
+/* ---- pairing / groth16.Verify --------------------------------------------------------------
+ * Replaces gnark-crypto bn254.MillerLoop / FinalExponentiation / PairingCheck (ecc/bn254/pairing.go, out of tree) under
+ * groth16.Verify -- src/prover/prover/prover.go:276, src/verifier/main.go:284.  Miller loops run one pair per GPU thread;
+ * the product and the one final exponentiation are O(1) host work.
+ * out_gt384 = prod_i e(P_i, Q_i) as 12 Montgomery Fp elements in gnark-crypto E12 memory order (C0.B0.A0 ... C1.B2.A1),
+ * raised to exactly (q^12-1)/r (gnark's GT value is a fixed power of this one; equalities between products agree). */
+int32_t zkpor_pairing_product(zkpor_ctx *ctx, const void *g1_points /* n x 64 B */, const void *g2_points /* n x 128 B */, uint64_t n,
+                              void *out_gt384 /* host */);
+/* *out_ok = 1 iff prod_i e(P_i, Q_i) == 1 (bn254.PairingCheck) */
+int32_t zkpor_pairing_check(zkpor_ctx *ctx, const void *g1_points, const void *g2_points, uint64_t n, int32_t *out_ok);
+
+/* groth16.VerifyingKey as gnark holds it in memory (points affine Montgomery; host pointers). */
+typedef struct {
+    const void *g1_alpha;                         /* vk.G1.Alpha                                                    */
+    const void *g2_beta, *g2_gamma, *g2_delta;    /* vk.G2.Beta / Gamma / Delta                                     */
+    const void *g1_k; uint64_t n_k;               /* vk.G1.K: ONE wire, public inputs, then one entry per commitment */
+    uint64_t n_commitments;                       /* len(vk.PublicAndCommitmentCommitted): 0 or 1 here              */
+    const uint64_t *public_committed;             /* vk.PublicAndCommitmentCommitted[0] (1-based public wire ids)   */
+    uint64_t n_public_committed;
+    const void *g2_ped_g, *g2_ped_g_root_sigma_neg;   /* vk.CommitmentKey.G / .GRootSigmaNeg (pedersen.VerifyingKey)  */
+} zkpor_vk_desc;
+/* groth16.Verify(proof, vk, publicWitness): proof = the bytes of proof.WriteRawTo (zkpor_groth16_prove's output),
+ * public_witness = n_public Montgomery fr.Elements (without the ONE wire).  Recomputes the BSB22 commitment challenge
+ * (hash_to_field, DST "bsb22-commitment"), checks the Pedersen proof of knowledge and the Groth16 pairing equation.
+ * *out_ok = 1 valid, 0 invalid (a malformed proof is an error return). */
+int32_t zkpor_groth16_verify(zkpor_ctx *ctx, const zkpor_vk_desc *vk, const uint8_t *proof_raw, uint32_t proof_len,
+                             const void *public_witness, uint64_t n_public, int32_t *out_ok);
+/* Batch verifier: `count` proofs of one circuit (proof i at proofs_raw + i*proof_stride, its public witness at
+ * public_witnesses + i*n_public*32) checked with ONE pairing product of count + 3 Miller loops: a random linear
+ * combination rho_i (derived from `seed32` and the proofs, 128-bit) folds the Groth16 equations; the Pedersen checks
+ * are folded the same way.  *out_ok = 1 iff every proof verifies (soundness error 2^-128 per batch). */
+int32_t zkpor_groth16_verify_batch(zkpor_ctx *ctx, const zkpor_vk_desc *vk, const uint8_t *proofs_raw, uint32_t proof_len,
+                                   uint64_t proof_stride, const void *public_witnesses, uint64_t n_public, uint64_t count,
+                                   const uint8_t seed32[32], int32_t *out_ok);
 
 /* ---- Poseidon / Merkle -----------------------------------------------------------------------------------------
  * Replaces the bnb-chain gnark-crypto fr/poseidon hashers (poseidon.Poseidon / PoseidonBytes / NewPoseidon, call

@@ -307,3 +307,24 @@ def check_in_exponent(cs: R1CS, toxic, proof, aux, r: int, s: int) -> bool:
     rhs = (al * be + (ksum_pub + kcommit) % R * ga_inv % R * ga + krs * de) % R
     ok &= lhs == rhs
     return bool(ok)
+
+
+# ----------------------------------------------------------------------------- Verify (gnark backend/groth16/bn254/verify.go restated)
+def verify(vk, proof, public_witness) -> bool:
+    """groth16.Verify (src/prover/prover/prover.go:276, src/verifier/main.go:284): recompute the commitment challenge,
+    check the Pedersen proof of knowledge e(C, G) e(pok, GRootSigmaNeg) = 1 (pok = sigma C, GRootSigmaNeg = G^(-1/sigma)) and
+    e(Krs, -delta) e(Ar, Bs) e(K0 + sum pw_i K_i + C, -gamma) = e(alpha, beta)."""
+    import pairing as pr
+    pw = list(public_witness)
+    ksum = vk["K"][0]
+    if proof["Commitments"]:
+        cpt = proof["Commitments"][0]
+        pw = pw + [commitment_challenge(cpt, [pw[i - 1] for i in vk["public_and_commitment_committed"][0]])]
+        if not pr.pairing_check([(cpt, vk["ped_g"]), (proof["CommitmentPok"], vk["ped_g_root_sigma_neg"])]):
+            return False
+        ksum = pt_add(ksum, cpt)
+    assert len(pw) == len(vk["K"]) - 1
+    for k, v in zip(vk["K"][1:], pw):
+        ksum = pt_add(ksum, pt_mul(k, v))
+    return pr.pairing_check([(proof["Krs"], bn.pt_neg(vk["delta2"], FP2)), (proof["Ar"], proof["Bs"]),
+                             (ksum, bn.pt_neg(vk["gamma2"], FP2)), (bn.pt_neg(vk["alpha1"]), vk["beta2"])])

@@ -61,20 +61,40 @@ def pk_arrays(sc, toxic):
                 delta2=orc.g2_fixed_base(lim([toxic["delta"]])), log_n=sc["log_n"])
 
 
-def synthetic_instance(n_constraints, nb_secret, seed):
-    """R1CS + key + solved witness, all via the oracle.  Returns dict with arrays in gnark memory layout."""
+def synthetic_instance(n_constraints, nb_secret, seed, input_seed=None):
+    """R1CS + key + solved witness, all via the oracle.  Returns dict with arrays in gnark memory layout.
+    input_seed: another assignment of the same circuit (same key)."""
     cs = g16.synth_r1cs(n_constraints, nb_secret, seed)
     tox = g16.toxic_from_seed(seed + 1)
     sc = g16.setup_scalars(cs, tox)
     arr = pk_arrays(sc, tox)
-    pub, sec = g16.synth_inputs(cs, seed + 2)
+    pub, sec = g16.synth_inputs(cs, seed + 2 if input_seed is None else input_seed)
     commit_fn = lambda vals: orc.g1_unpack(orc.g1_msm(arr["ck_basis"], orc.fr_mont(vals)))[0]
     w, a, b, c, cpt, cvals = g16.solve(cs, None, pub, sec, commit_fn)
     wa = [w[i] for i in range(len(w)) if not sc["infinity_a"][i]]
     wb = [w[i] for i in range(len(w)) if not sc["infinity_b"][i]]
     drop = set(cs.private_committed) | {cs.commitment_index}
     wk = [w[i] for i in range(cs.nb_public, len(w)) if i not in drop]
-    return dict(cs=cs, tox=tox, sc=sc, arr=arr, w=w, a=a, b=b, c=c, wa=wa, wb=wb, wk=wk, committed=cvals, commitment=cpt)
+    return dict(cs=cs, tox=tox, sc=sc, arr=arr, w=w, a=a, b=b, c=c, wa=wa, wb=wb, wk=wk, committed=cvals, commitment=cpt, vk=oracle_vk(cs, sc, tox))
+
+
+def oracle_vk(cs, sc, tox):
+    """groth16.VerifyingKey as Python points (the dict oracle/py/groth16.py verify() takes), from the setup scalars"""
+    from bn254 import FP2, G1_GEN, G2_GEN, pt_mul
+    g1 = lambda s: pt_mul(G1_GEN, s)
+    g2 = lambda s: pt_mul(G2_GEN, s, FP2)
+    ped_g = g2(tox["ped_g2"])
+    return dict(alpha1=g1(tox["alpha"]), beta2=g2(tox["beta"]), gamma2=g2(tox["gamma"]), delta2=g2(tox["delta"]),
+                K=[g1(s) for s in sc["vkK_s"]], ped_g=ped_g, ped_g_root_sigma_neg=pt_mul(ped_g, (-pow(tox["sigma"], -1, R)) % R, FP2),
+                public_and_commitment_committed=[[]] if cs.commitment_index >= 0 else [])
+
+
+def vk_arrays(inst):
+    """keyword arguments of zkpor_b200.VerifyingKey (numpy, gnark memory layout) for a synthetic instance"""
+    vk = inst["vk"]
+    return dict(alpha1=orc.g1_pack([vk["alpha1"]]), beta2=orc.g2_pack([vk["beta2"]]), gamma2=orc.g2_pack([vk["gamma2"]]),
+                delta2=orc.g2_pack([vk["delta2"]]), K=orc.g1_pack(vk["K"]), n_commitments=len(vk["public_and_commitment_committed"]),
+                public_committed=(), ped_g=orc.g2_pack([vk["ped_g"]]), ped_g_root_sigma_neg=orc.g2_pack([vk["ped_g_root_sigma_neg"]]))
 
 
 def oracle_proof(inst, r, s):

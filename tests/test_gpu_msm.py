@@ -64,6 +64,51 @@ def test_edge_cases(ctx):
     assert np.array_equal(ctx.msm_g1(pts, sc2, n), orc.g1_msm(pts, sc2))
 
 
+@pytest.mark.parametrize("rounds", [0, 1, 2, 3, -1])
+def test_affine_tree_special_cases(ctx, rounds):
+    """Bucket lists full of repeated points, opposite points and infinities: every pair class of the batched-affine
+    tree (doubling, cancellation to infinity, infinity operands, odd element carried over) at every tree depth, and
+    the extended-Jacobian-only path (rounds = 0), all bit-exact against the oracle."""
+    n = 6000
+    rng = SplitMix64(77)
+    base = g1_points(6, 70)
+    neg = orc.g1_pack([bn.pt_neg(q) for q in orc.g1_unpack(base)])
+    pool = np.concatenate([base, neg, np.zeros((1, 8), dtype=np.uint64)])          # 6 points, their negatives, infinity
+    pts = np.ascontiguousarray(pool[[rng.next() % len(pool) for _ in range(n)]])
+    svals = [3, 3, 3, R - 3, 0x10001, (1 << 200) + 17, R - 1, 1]                       # few distinct scalars -> few, long bucket lists
+    ss = [svals[rng.next() % len(svals)] for _ in range(n)]
+    sc = orc.fr_mont(ss)
+    want = orc.g1_msm(pts, sc)
+    ctx.set_affine_rounds(rounds)
+    try:
+        assert np.array_equal(ctx.msm_g1(pts, sc, n), want)
+        # mixed with uniform scalars (lists of ordinary length next to the degenerate ones)
+        ss2 = [ss[i] if i % 3 else rng.field(R) for i in range(n)]
+        sc2 = orc.fr_mont(ss2)
+        assert np.array_equal(ctx.msm_g1(pts, sc2, n), orc.g1_msm(pts, sc2))
+        b2 = g2_points(5, 71)
+        neg2 = orc.g2_pack([bn.pt_neg(q, FP2) for q in orc.g2_unpack(b2)])
+        pool2 = np.concatenate([b2, neg2, np.zeros((1, 16), dtype=np.uint64)])
+        n2 = 3000
+        p2 = np.ascontiguousarray(pool2[[rng.next() % len(pool2) for _ in range(n2)]])
+        s2 = orc.fr_mont([svals[rng.next() % len(svals)] if i % 4 else rng.field(R) for i in range(n2)])
+        assert np.array_equal(ctx.msm_g2(p2, s2, n2), orc.g2_msm(p2, s2))
+    finally:
+        ctx.set_affine_rounds(0)
+
+
+@pytest.mark.parametrize("rounds", [0, 2, -1])
+def test_affine_rounds_agree_at_2pow18(ctx, rounds):
+    n = 1 << 18
+    pts = g1_points(2048, 81); pts = np.ascontiguousarray(np.tile(pts, (n // 2048, 1)))
+    sc = rand_scalars_np(n, 82)
+    ctx.set_affine_rounds(rounds)
+    try:
+        assert np.array_equal(ctx.msm_g1(pts, sc, n), orc.g1_msm(pts, sc))
+    finally:
+        ctx.set_affine_rounds(0)
+
+
 def test_heavy_buckets_skewed_witness(ctx):
     """witness-like scalars at a size where one bucket (the value 1) holds far more than the heavy threshold"""
     n = 150000

@@ -69,6 +69,24 @@ def test_fr_add_sub_neg_inv(ht):
         assert orc.fr_unmont(o)[0] == (pow(a, -1, R) if a else 0)
 
 
+@pytest.mark.parametrize("which", [0, 1])
+def test_divstep_inverse_matches_fermat_and_python(ht, which):
+    """Fe::inv (Bernstein-Yang divsteps on 30-bit limbs, ff.cuh) against Fermat in the same header and Python's pow."""
+    mod = P if which == 0 else R
+    rng = SplitMix64(17 + which)
+    vals = edge_values(mod) + [3, (1 << 30) - 1, 1 << 30, 1 << 60, (mod >> 1) + 1] + [rng.field(mod) for _ in range(1500)]
+    vals += [rng.field(1 << k) for k in range(1, 254)]
+    arr = orc.ints_to_limbs(vals)
+    assert ht.ht_inv_crosscheck(p(arr), len(vals), which) == 0
+    fn = ht.ht_fp_inv if which == 0 else ht.ht_fr_inv
+    rinv = pow(bn.MONT_R, -1, mod)
+    for v in vals[:60]:
+        o = np.zeros(4, dtype=np.uint64)
+        fn(p(orc.ints_to_limbs([v])), p(o))
+        plain = v * rinv % mod
+        assert orc.limbs_to_ints(o)[0] == (pow(plain, -1, mod) * bn.MONT_R % mod if plain else 0)
+
+
 def test_xyzz_accumulate_g1_g2(ht):
     rng = SplitMix64(9)
     ks = [1 + rng.field(R - 1) for _ in range(12)]
@@ -102,3 +120,29 @@ def test_xyzz_add_mul(ht):
             assert unpack(oa)[0] == bn.pt_mul(gen, k1 + k2, F)
             assert unpack(om)[0] == bn.pt_mul(gen, k1 * k3, F)
             assert unpack(od)[0] == bn.pt_mul(gen, 2 * k1, F)
+
+
+def test_pairing_header_matches_oracle(ht):
+    """csrc/pairing.cuh through its __host__ path: Fp12 tower arithmetic, the Miller loop value and e(P, Q), bit for bit
+    against oracle/py/pairing.py (dense-polynomial Fp12, generic line functions)."""
+    import pairing as pr
+
+    def to_arr(t):
+        return orc.fp_mont([v for c in t for b in c for v in b])
+
+    def from_arr(a):
+        v = orc.fp_unmont(a.reshape(12, 4))
+        return pr.from_tower(tuple(tuple((v[6 * i + 2 * j], v[6 * i + 2 * j + 1]) for j in range(3)) for i in range(2)))
+
+    rng = SplitMix64(4)
+    x = tuple(rng.field(P) for _ in range(12)); y = tuple(rng.field(P) for _ in range(12))
+    om, osq, oi = (np.zeros(48, dtype=np.uint64) for _ in range(3))
+    ht.ht_fp12_ops(p(to_arr(pr.to_tower(x))), p(to_arr(pr.to_tower(y))), p(om), p(osq), p(oi))
+    assert from_arr(om) == pr.f12_mul(x, y) and from_arr(osq) == pr.f12_sqr(x) and from_arr(oi) == pr.f12_inv(x)
+    a, b = rng.field(R), rng.field(R)
+    pa = bn.pt_mul(G1_GEN, a); qb = bn.pt_mul(G2_GEN, b, FP2)
+    mil, gt = np.zeros(48, dtype=np.uint64), np.zeros(48, dtype=np.uint64)
+    ht.ht_pairing(p(orc.g1_pack([pa])), p(orc.g2_pack([qb])), p(mil), p(gt))
+    want_m = pr.miller_loop(pr.untwist(qb), pr.embed_g1(pa))
+    assert from_arr(mil) == want_m
+    assert from_arr(gt) == pr.final_exponentiation(want_m)

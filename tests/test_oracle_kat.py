@@ -134,3 +134,37 @@ def test_sparse_partial_round_form_equals_textbook_permutation():
         st = [rng.field(R) for _ in range(t)]
         assert ps.permute_sparse(st) == ps.permute(st)
     assert ps.permute_sparse([0, 1, 2])[0] == 7853200120776062878684798364095072458815029376092732009249414926327459813530
+
+
+# ----------------------------------------------------------------------------- pairing / Verify (oracle/py/pairing.py)
+def test_pairing_bilinear_nondegenerate_order_r():
+    import pairing as pr
+    from bn254 import FP2, G1_GEN, G2_GEN, pt_mul, pt_neg
+    e = pr.pairing(G1_GEN, G2_GEN)
+    assert e != pr.F12_ONE and pr.f12_pow(e, R) == pr.F12_ONE
+    a, b = 0x1234567, 0x89ABCDEF01
+    assert pr.pairing(pt_mul(G1_GEN, a), pt_mul(G2_GEN, b, FP2)) == pr.f12_pow(e, a * b % R)
+    assert pr.pairing_check([(pt_mul(G1_GEN, a), G2_GEN), (pt_neg(G1_GEN), pt_mul(G2_GEN, a, FP2))])
+    assert not pr.pairing_check([(pt_mul(G1_GEN, a), G2_GEN), (pt_neg(G1_GEN), pt_mul(G2_GEN, a + 1, FP2))])
+    assert pr.pairing(None, G2_GEN) == pr.F12_ONE and pr.pairing(G1_GEN, None) == pr.F12_ONE
+    x = pr.f12(range(3, 15))
+    assert pr.from_tower(pr.to_tower(x)) == x and pr.f12_mul(x, pr.f12_inv(x)) == pr.F12_ONE
+
+
+def test_oracle_verify_accepts_and_rejects():
+    import groth16 as g16
+    from bn254 import G1_GEN, SplitMix64, pt_add
+    cs = g16.synth_r1cs(60, 8, seed=3)
+    tox = g16.toxic_from_seed(4)
+    pk, vk = g16.setup(cs, tox)
+    pub, sec = g16.synth_inputs(cs, 5)
+    rng = SplitMix64(9)
+    r, s = rng.field(R), rng.field(R)
+    proof, aux = g16.prove(cs, pk, pub, sec, r, s)
+    assert g16.check_in_exponent(cs, tox, proof, aux, r, s)      # toxic-waste check and pairing check agree
+    assert g16.verify(vk, proof, pub)
+    bad = dict(proof); bad["Krs"] = pt_add(proof["Krs"], G1_GEN)
+    assert not g16.verify(vk, bad, pub)
+    assert not g16.verify(vk, proof, [(pub[0] + 1) % R] + list(pub[1:]))
+    bad = dict(proof); bad["CommitmentPok"] = pt_add(proof["CommitmentPok"], G1_GEN)
+    assert not g16.verify(vk, bad, pub)

@@ -169,6 +169,10 @@ class Context:
         return dict(total_ms=ms.value, launches=n.value, units=u.value)
 
     # --- MSM
+    def set_affine_rounds(self, rounds: int):
+        """Levels of batched-affine tree summation per bucket (0 = extended-Jacobian only, the default; -1 automatic; k > 0 at most k)."""
+        _check(lib().zkpor_msm_set_affine_rounds(self._h, C.c_int32(rounds)))
+
     def msm_g1(self, points, scalars, n: int, flags: int = ZKPOR_SCALARS_MONT) -> np.ndarray:
         out = np.zeros(8, dtype=np.uint64)
         _check(lib().zkpor_msm_g1(self._h, _ptr(points), _ptr(scalars), C.c_uint64(n), C.c_uint32(flags), _ptr(out)))
@@ -552,6 +556,61 @@ def groth16_setup(ctx: Context, log_n: int, n_wires: int, nb_public: int, csc_a,
         pk_kwargs.update(ck_basis=fb(ck_s), ck_basis_exp_sigma=fb(ck_sigma_s), private_committed=committed.astype(np.uint64), commitment_index=commitment_index)
     extras = dict(vk_K=fb(vk_s), gamma2=one(toxic["gamma"], True), n_vk=int(vk_s.shape[0]))
     return pk_kwargs, extras
+
+
+# ----------------------------------------------------------------------------------------------- pairing / Verify
+class VkDesc(C.Structure):
+    _fields_ = [("g1_alpha", C.c_void_p), ("g2_beta", C.c_void_p), ("g2_gamma", C.c_void_p), ("g2_delta", C.c_void_p),
+                ("g1_k", C.c_void_p), ("n_k", C.c_uint64), ("n_commitments", C.c_uint64),
+                ("public_committed", C.c_void_p), ("n_public_committed", C.c_uint64),
+                ("g2_ped_g", C.c_void_p), ("g2_ped_g_root_sigma_neg", C.c_void_p)]
+
+
+def pairing_product(ctx: Context, g1_points, g2_points, n: int) -> np.ndarray:
+    """prod_i e(P_i, Q_i) as (12, 4) uint64: Montgomery Fp limbs in gnark-crypto E12 order (bn254.Pair)."""
+    out = np.zeros((12, 4), dtype=np.uint64)
+    _check(lib().zkpor_pairing_product(ctx._h, _ptr(g1_points), _ptr(g2_points), C.c_uint64(n), _ptr(out)))
+    return out
+
+
+def pairing_check(ctx: Context, g1_points, g2_points, n: int) -> bool:
+    ok = C.c_int32(0)
+    _check(lib().zkpor_pairing_check(ctx._h, _ptr(g1_points), _ptr(g2_points), C.c_uint64(n), C.byref(ok)))
+    return bool(ok.value)
+
+
+class VerifyingKey:
+    """groth16.VerifyingKey (what vk.ReadFrom fills at src/verifier/main.go:33-34): numpy uint64 arrays in gnark memory
+    layout.  K = vk.G1.K (ONE wire, public inputs, commitment wire)."""
+
+    def __init__(self, *, alpha1, beta2, gamma2, delta2, K, n_commitments=1, public_committed=(), ped_g=None, ped_g_root_sigma_neg=None):
+        h = lambda x: None if x is None else np.ascontiguousarray(x, dtype=np.uint64)
+        self._keep = dict(alpha1=h(alpha1), beta2=h(beta2), gamma2=h(gamma2), delta2=h(delta2), K=h(K), ped_g=h(ped_g), grsn=h(ped_g_root_sigma_neg),
+                          pc=np.ascontiguousarray(public_committed, dtype=np.uint64))
+        k = self._keep
+        self.desc = VkDesc(_ptr(k["alpha1"]), _ptr(k["beta2"]), _ptr(k["gamma2"]), _ptr(k["delta2"]), _ptr(k["K"]), k["K"].reshape(-1, 8).shape[0],
+                           n_commitments, _ptr(k["pc"]) if k["pc"].size else None, k["pc"].size, _ptr(k["ped_g"]), _ptr(k["grsn"]))
+
+    def verify(self, ctx: Context, proof_raw: bytes, public_witness) -> bool:
+        """groth16.Verify(proof, vk, publicWitness) (prover.go:276, verifier/main.go:284); public_witness = (n, 4) uint64 Montgomery."""
+        pw = np.ascontiguousarray(public_witness, dtype=np.uint64).reshape(-1, 4)
+        buf = np.frombuffer(proof_raw, dtype=np.uint8).copy()
+        ok = C.c_int32(0)
+        _check(lib().zkpor_groth16_verify(ctx._h, C.byref(self.desc), _ptr(buf), C.c_uint32(buf.size), _ptr(pw) if pw.size else None,
+                                          C.c_uint64(pw.shape[0]), C.byref(ok)))
+        return bool(ok.value)
+
+    def verify_batch(self, ctx: Context, proofs_raw, public_witnesses, seed: bytes = bytes(32)) -> bool:
+        """all proofs of one circuit with one pairing product (random linear combination bound to `seed` and the batch)"""
+        count = len(proofs_raw)
+        plen = len(proofs_raw[0])
+        buf = np.frombuffer(b"".join(proofs_raw), dtype=np.uint8).copy()
+        pw = np.ascontiguousarray(public_witnesses, dtype=np.uint64).reshape(count, -1, 4)
+        sd = np.frombuffer(seed, dtype=np.uint8).copy()
+        ok = C.c_int32(0)
+        _check(lib().zkpor_groth16_verify_batch(ctx._h, C.byref(self.desc), _ptr(buf), C.c_uint32(plen), C.c_uint64(plen), _ptr(pw) if pw.size else None,
+                                                C.c_uint64(pw.shape[1]), C.c_uint64(count), _ptr(sd), C.byref(ok)))
+        return bool(ok.value)
 
 
 # ----------------------------------------------------------------------------------------------- multi-GPU host logic

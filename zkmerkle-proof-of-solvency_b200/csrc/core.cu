@@ -1,5 +1,6 @@
 // Context lifecycle, error reporting and small host helpers of libzkpor_b200.
 #include "internal.h"
+#include <cstdlib>
 
 namespace zk {
 
@@ -73,6 +74,8 @@ int32_t zkpor_ctx_create(int32_t device_id, zkpor_ctx **out) {
     zkpor_ctx *ctx = new zkpor_ctx();
     ctx->device = device_id;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *v = getenv("ZKPOR_AFFINE_ROUNDS")) ctx->affine_rounds = atoi(v);
+    if (const char *v = getenv("ZKPOR_G2_TIGHT")) ctx->g2_tight_regs = atoi(v) != 0;
     ZK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ZK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     ZK_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
@@ -93,7 +96,7 @@ int32_t zkpor_ctx_destroy(zkpor_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
     zk::DevBuf *bufs[] = {&ctx->in_points, &ctx->in_scalars, &ctx->sort_idx, &ctx->bucket_cnt, &ctx->bucket_off, &ctx->bucket_cur,
-                          &ctx->buckets, &ctx->partials, &ctx->windows, &ctx->misc, &ctx->ntt_a, &ctx->ntt_b, &ctx->ntt_c, &ctx->io, &ctx->heavy, &ctx->heavy_part, &ctx->order};
+                          &ctx->buckets, &ctx->partials, &ctx->windows, &ctx->misc, &ctx->ntt_a, &ctx->ntt_b, &ctx->ntt_c, &ctx->io, &ctx->heavy, &ctx->heavy_part, &ctx->order, &ctx->tree_a, &ctx->tree_b, &ctx->tree_meta};
     for (auto *b : bufs) b->release();
     zk_free_poseidon(ctx); zk_free_ntt(ctx);
     for (auto &r : ctx->klog) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -110,6 +113,11 @@ int32_t zkpor_ctx_destroy(zkpor_ctx *ctx) {
 int32_t zkpor_ctx_sync(zkpor_ctx *ctx) {
     ZK_REQUIRE(ctx != nullptr, "ctx_sync: null context");
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKPOR_OK;
+}
+int32_t zkpor_msm_set_affine_rounds(zkpor_ctx *ctx, int32_t rounds) {
+    ZK_REQUIRE(ctx != nullptr, "msm_set_affine_rounds: null context");
+    ctx->affine_rounds = rounds;
     return ZKPOR_OK;
 }
 int32_t zkpor_ctx_launch_count(zkpor_ctx *ctx, uint64_t *out) {

@@ -26,12 +26,19 @@ struct FpParams {   // base field q
     static constexpr uint32_t INV = 0xe4866389u;   // -q^-1 mod 2^32
     FF_HD static constexpr uint32_t R2(int i) { constexpr uint32_t t[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u}; return t[i]; }
     FF_HD static constexpr uint32_t ONE(int i) { constexpr uint32_t t[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}; return t[i]; }
+    // R^3 mod q, the modulus in 9 x 30-bit limbs and q^-1 mod 2^30: constants of the divstep inversion (Fe::inv)
+    FF_HD static constexpr uint32_t R3(int i) { constexpr uint32_t t[8] = {0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u, 0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u}; return t[i]; }
+    FF_HD static constexpr int32_t M30(int i) { constexpr int32_t t[9] = {0x187cfd47, 0x3082305b, 0x71ca8d3, 0x205aa45a, 0x1585d97, 0x116da06, 0x1a029b85, 0x139cb84c, 0x3064}; return t[i]; }
+    static constexpr uint32_t INV30 = 0x1b799c77u;
 };
 struct FrParams {   // scalar field r
     FF_HD static constexpr uint32_t M(int i) { constexpr uint32_t t[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u}; return t[i]; }
     static constexpr uint32_t INV = 0xefffffffu;
     FF_HD static constexpr uint32_t R2(int i) { constexpr uint32_t t[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u}; return t[i]; }
     FF_HD static constexpr uint32_t ONE(int i) { constexpr uint32_t t[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}; return t[i]; }
+    FF_HD static constexpr uint32_t R3(int i) { constexpr uint32_t t[8] = {0xb4bf0040u, 0x5e94d8e1u, 0x1cfbb6b8u, 0x2a489cbeu, 0xa19fcfedu, 0x893cc664u, 0x7fcc657cu, 0x0cf8594bu}; return t[i]; }
+    FF_HD static constexpr int32_t M30(int i) { constexpr int32_t t[9] = {0x30000001, 0xf87d64f, 0x1b970914, 0xcfa121e, 0x1585d28, 0x116da06, 0x1a029b85, 0x139cb84c, 0x3064}; return t[i]; }
+    static constexpr uint32_t INV30 = 0x10000001u;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX carry chains
@@ -359,11 +366,116 @@ struct alignas(16) Fe {
         }
         return acc;
     }
-    FF_HD static Fe inv(const Fe &a) {   // Fermat; inv(0) = 0
+    FF_HD static Fe inv_fermat(const Fe &a) {   // a^(m-2); inv(0) = 0.  Kept as the cross-check of inv()
         uint32_t e[8];
         for (int i = 0; i < 8; i++) e[i] = P::M(i);
         e[0] -= 2;   // both moduli are odd with low limb >= 2
         return pow(a, e);
+    }
+
+    // ---- inversion by divsteps (Bernstein-Yang "safegcd", half-delta variant) ------------------------------------
+    // 20 rounds of 30 divsteps on the low words of (f, g) = (m, a), each round followed by the 2x2 transition matrix
+    // applied to the full-width (f, g) and, modulo m, to (d, e) -- numbers held as 9 signed 30-bit limbs.  600 divsteps
+    // cover every input below 2^256; control flow is data-independent, so the 32 lanes of a warp never diverge.
+    // Cost: ~1800 32x32->64 multiply-adds + ~10^4 ALU-pipe instructions, i.e. the IMAD-pipe time of ~15 field
+    // products (Fermat: ~320 products).  This is what makes batched-affine bucket accumulation pay (msm.cu).
+    FF_HD static int32_t divsteps30(int32_t zeta, uint32_t f, uint32_t g, int32_t (&t)[4]) {
+        uint32_t u = 1, v = 0, q = 0, r = 1;
+#pragma unroll 6
+        for (int i = 0; i < 30; i++) {
+            uint32_t c1 = (uint32_t)(zeta >> 31), c2 = 0u - (g & 1u);
+            uint32_t x = (f ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;
+            g += x & c2; q += y & c2; r += z & c2;
+            c1 &= c2;
+            zeta = (zeta ^ (int32_t)c1) - 1;
+            f += g & c1; u += q & c1; v += r & c1;
+            g >>= 1; u <<= 1; v <<= 1;
+        }
+        t[0] = (int32_t)u; t[1] = (int32_t)v; t[2] = (int32_t)q; t[3] = (int32_t)r;
+        return zeta;
+    }
+    FF_HD static Fe inv(const Fe &a) {   // inv(0) = 0
+        const int32_t M30 = 0x3fffffff;
+        int32_t d[9], e[9], f[9], g[9];
+        // a (8 x 32 bits) -> 9 x 30 bits
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const int bit = 30 * i, w = bit >> 5, s = bit & 31;
+            uint64_t lo = a.l[w], hi = (w + 1 < 8) ? a.l[w + 1] : 0u;
+            g[i] = (int32_t)(((lo | (hi << 32)) >> s) & (uint64_t)M30);
+            f[i] = P::M30(i); d[i] = 0; e[i] = 0;
+        }
+        e[0] = 1;
+        int32_t zeta = -1;
+        for (int it = 0; it < 20; it++) {
+            int32_t t[4];
+            zeta = divsteps30(zeta, (uint32_t)f[0], (uint32_t)g[0], t);
+            const int32_t u = t[0], v = t[1], q = t[2], r = t[3];
+            // every product below is int32 x int32 -> int64 (one IMAD.WIDE with the 64-bit accumulator as addend)
+#define FF_MW(a, b) ((int64_t)(a) * (int64_t)(b))
+            // (d, e) <- t * (d, e) / 2^30 mod m: multiples of m are added so that the low 30 bits cancel
+            {
+                const int32_t sd = d[8] >> 31, se = e[8] >> 31;
+                int32_t md = (u & sd) + (v & se), me = (q & sd) + (r & se);
+                int64_t cd = FF_MW(u, d[0]) + FF_MW(v, e[0]), ce = FF_MW(q, d[0]) + FF_MW(r, e[0]);
+                md -= (int32_t)((P::INV30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+                me -= (int32_t)((P::INV30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+                cd += FF_MW(P::M30(0), md); ce += FF_MW(P::M30(0), me);
+                cd >>= 30; ce >>= 30;
+#pragma unroll
+                for (int i = 1; i < 9; i++) {
+                    cd += FF_MW(u, d[i]) + FF_MW(v, e[i]) + FF_MW(P::M30(i), md);
+                    ce += FF_MW(q, d[i]) + FF_MW(r, e[i]) + FF_MW(P::M30(i), me);
+                    d[i - 1] = (int32_t)cd & M30; cd >>= 30;
+                    e[i - 1] = (int32_t)ce & M30; ce >>= 30;
+                }
+                d[8] = (int32_t)cd; e[8] = (int32_t)ce;
+            }
+            // (f, g) <- t * (f, g) / 2^30 (exact)
+            {
+                int64_t cf = FF_MW(u, f[0]) + FF_MW(v, g[0]), cg = FF_MW(q, f[0]) + FF_MW(r, g[0]);
+                cf >>= 30; cg >>= 30;
+#pragma unroll
+                for (int i = 1; i < 9; i++) {
+                    cf += FF_MW(u, f[i]) + FF_MW(v, g[i]);
+                    cg += FF_MW(q, f[i]) + FF_MW(r, g[i]);
+                    f[i - 1] = (int32_t)cf & M30; cf >>= 30;
+                    g[i - 1] = (int32_t)cg & M30; cg >>= 30;
+                }
+                f[8] = (int32_t)cf; g[8] = (int32_t)cg;
+            }
+#undef FF_MW
+        }
+        // now g = 0 and f = +/- gcd = +/- 1 (or +/- m when a = 0): a^-1 = sign(f) * d, brought to [0, m)
+        {
+            int32_t add = d[8] >> 31;
+#pragma unroll
+            for (int i = 0; i < 9; i++) d[i] += P::M30(i) & add;
+            const int32_t ng = f[8] >> 31;
+#pragma unroll
+            for (int i = 0; i < 9; i++) d[i] = (d[i] ^ ng) - ng;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { d[i + 1] += d[i] >> 30; d[i] &= M30; }
+            add = d[8] >> 31;
+#pragma unroll
+            for (int i = 0; i < 9; i++) d[i] += P::M30(i) & add;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { d[i + 1] += d[i] >> 30; d[i] &= M30; }
+        }
+        // 9 x 30 bits -> 8 x 32 bits; the plain inverse of (a R) is a^-1 R^-1, one product by R^3 restores a^-1 R
+        Fe o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int bit = 32 * i, w = bit / 30, s = bit % 30;
+            uint64_t acc = (uint64_t)(uint32_t)d[w] >> s;
+            acc |= (uint64_t)(uint32_t)d[w + 1] << (30 - s);
+            if (w + 2 < 9 && 60 - s < 32) acc |= (uint64_t)(uint32_t)d[w + 2] << (60 - s);
+            o.l[i] = (uint32_t)acc;
+        }
+        Fe r3;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r3.l[i] = P::R3(i);
+        return mul(o, r3);
     }
     FF_HD static Fe from_u64(uint64_t v) { Fe o = zero(); o.l[0] = (uint32_t)v; o.l[1] = (uint32_t)(v >> 32); return to_mont(o); }
 };

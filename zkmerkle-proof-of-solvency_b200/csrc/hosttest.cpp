@@ -2,7 +2,7 @@
 // tests/test_host_ff.py through ctypes so that the limb schedule of Fe::mul and the XYZZ formulas are checked on the
 // CPU against the oracle before any GPU time is spent.
 #define FF_HOST_EMULATE_PTX 1
-#include "ec.cuh"
+#include "pairing.cuh"
 using namespace ff;
 using namespace ec;
 extern "C" {
@@ -21,6 +21,16 @@ void ht_fr_addsub(const uint32_t *a, const uint32_t *b, uint32_t *oadd, uint32_t
     Fr s = Fr::add(x, y), d = Fr::sub(x, y), n = Fr::neg(x); memcpy(oadd, &s, 32); memcpy(osub, &d, 32); memcpy(oneg, &n, 32);
 }
 void ht_fr_inv(const uint32_t *a, uint32_t *o) { Fr x; memcpy(&x, a, 32); Fr r = Fr::inv(x); memcpy(o, &r, 32); }
+void ht_fp_inv(const uint32_t *a, uint32_t *o) { Fp x; memcpy(&x, a, 32); Fp r = Fp::inv(x); memcpy(o, &r, 32); }
+// divstep inversion against Fermat on n values (32 bytes each, already reduced); returns the number of mismatches
+int ht_inv_crosscheck(const uint32_t *vals, int n, int which) {
+    int bad = 0;
+    for (int i = 0; i < n; i++) {
+        if (which == 0) { Fp x; memcpy(&x, vals + 8 * i, 32); bad += !(Fp::inv(x) == Fp::inv_fermat(x)); }
+        else { Fr x; memcpy(&x, vals + 8 * i, 32); bad += !(Fr::inv(x) == Fr::inv_fermat(x)); }
+    }
+    return bad;
+}
 // sum_i (+/-) p_i accumulated with add_affine, then a general add of the accumulator with itself-shifted copy
 void ht_g1_accumulate(const uint32_t *pts, const uint8_t *neg, int n, uint32_t *out_aff) {
     G1XYZZ acc = G1XYZZ::inf();
@@ -45,5 +55,18 @@ void ht_g2_add_mul(const uint32_t *p, const uint32_t *q, const uint32_t *k, uint
     G2XYZZ s = x; s.add(y); G2Affine r = s.to_affine(); memcpy(out_add, &r, 128);
     r = x.mul_256(k).to_affine(); memcpy(out_mul, &r, 128);
     G2XYZZ d = x; d.add(x); r = d.to_affine(); memcpy(out_dbl, &r, 128);
+}
+// pairing: Miller loop value and e(P, Q) = miller^((q^12-1)/r), both as 12 Fp Montgomery elements in tower order
+void ht_pairing(const uint32_t *p, const uint32_t *q, uint32_t *out_miller, uint32_t *out_gt) {
+    G1Affine a; G2Affine b; memcpy(&a, p, 64); memcpy(&b, q, 128);
+    pairing::Fp12 f = pairing::miller_loop(a, b);
+    memcpy(out_miller, &f, 384);
+    pairing::Fp12 e = pairing::final_exponentiation(f);
+    memcpy(out_gt, &e, 384);
+}
+void ht_fp12_ops(const uint32_t *a, const uint32_t *b, uint32_t *out_mul, uint32_t *out_sqr, uint32_t *out_inv) {
+    pairing::Fp12 x, y; memcpy(&x, a, 384); memcpy(&y, b, 384);
+    pairing::Fp12 m = pairing::Fp12::mul(x, y), s = pairing::Fp12::sqr(x), i = pairing::Fp12::inv(x);
+    memcpy(out_mul, &m, 384); memcpy(out_sqr, &s, 384); memcpy(out_inv, &i, 384);
 }
 }

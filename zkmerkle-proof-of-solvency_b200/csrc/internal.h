@@ -15,14 +15,22 @@ MsmPlan msm_plan(uint64_t n);
 // cut into blocks of HEAVY_CHUNK references, each reduced by a whole CTA; see k_heavy_plan in msm.cu.
 struct HeavyBlk { uint32_t slot, start, count; };
 struct HeavyBkt { uint32_t slot, first_blk, nblk; };
+// Population bins of the bucket schedule: slots (window, bucket) are ordered by decreasing reference count with a counting
+// sort over SIZE_BINS exact bins (heavy buckets, > heavy_t <= SIZE_BINS - 2 references, share the last bin).
+static const uint32_t SIZE_BINS = 8192;
 struct MsmSorted {
     MsmPlan plan; uint64_t n; const uint32_t *idx, *off, *cnt, *order;   // order: slots by decreasing population
+    const uint32_t *hist, *bin_start;   // slots per population bin; first position of a bin in `order`
     uint32_t heavy_t, max_blks, max_bkts; const HeavyBlk *blks; const HeavyBkt *bkts; const uint32_t *counters;
 };
 
 int32_t msm_sort(zkpor_ctx *ctx, const void *d_scalars, uint64_t n, uint32_t flags, MsmSorted *out);
 int32_t msm_accumulate_g1(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, ec::G1XYZZ *host_out);
 int32_t msm_accumulate_g2(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, ec::G2XYZZ *host_out);
+// sums of the light buckets (cnt <= heavy_t) by batched-affine tree rounds + an XYZZ tail (msm_affine.cu); *done = false
+// when the lists are too short for it to pay (or HBM is short) and the caller must run the XYZZ accumulation instead
+int32_t msm_tree_sums(zkpor_ctx *ctx, const ec::G1Affine *d_points, const MsmSorted &s, ec::G1XYZZ *buckets, bool *done);
+int32_t msm_tree_sums(zkpor_ctx *ctx, const ec::G2Affine *d_points, const MsmSorted &s, ec::G2XYZZ *buckets, bool *done);
 // full device MSM on device-resident inputs; result as XYZZ on the host
 int32_t msm_g1_dev(zkpor_ctx *ctx, const void *d_points, const void *d_scalars, uint64_t n, uint32_t flags, ec::G1XYZZ *host_out);
 int32_t msm_g2_dev(zkpor_ctx *ctx, const void *d_points, const void *d_scalars, uint64_t n, uint32_t flags, ec::G2XYZZ *host_out);

@@ -155,7 +155,6 @@ __global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict_
 // Threads of a warp run until the fullest of their 32 buckets is done (ncu, first version: 22 of 32 lanes active on
 // average).  Buckets are therefore handed to threads in order of decreasing population: a counting sort of the
 // (window, bucket) slots by their reference count, so that the 32 buckets of a warp have (almost) equal length.
-static const uint32_t SIZE_BINS = 2048;
 
 __global__ void k_size_hist(const uint32_t *__restrict__ cnt, size_t slots, uint32_t *__restrict__ hist) {
     __shared__ uint32_t sh[SIZE_BINS];
@@ -169,13 +168,13 @@ __global__ void k_size_hist(const uint32_t *__restrict__ cnt, size_t slots, uint
     for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 // cursor[b] = number of slots in bins above b (descending order); one block of SIZE_BINS/2 threads, trivial size
-__global__ void k_size_scan(const uint32_t *__restrict__ hist, uint32_t *__restrict__ cursor) {
+__global__ void k_size_scan(const uint32_t *__restrict__ hist, uint32_t *__restrict__ cursor, uint32_t *__restrict__ bin_start) {
     __shared__ uint32_t sh[SIZE_BINS];
     for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) sh[i] = hist[SIZE_BINS - 1 - i];   // reversed
     __syncthreads();
     if (threadIdx.x == 0) { uint32_t run = 0; for (uint32_t i = 0; i < SIZE_BINS; i++) { uint32_t v = sh[i]; sh[i] = run; run += v; } }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) cursor[SIZE_BINS - 1 - i] = sh[i];
+    for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) { cursor[SIZE_BINS - 1 - i] = sh[i]; bin_start[SIZE_BINS - 1 - i] = sh[i]; }
 }
 __global__ void k_size_scatter(const uint32_t *__restrict__ cnt, size_t slots, uint32_t *__restrict__ cursor, uint32_t *__restrict__ order) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,7 +310,10 @@ int32_t msm_sort(zkpor_ctx *ctx, const void *d_scalars, uint64_t n, uint32_t fla
     // heavy-bucket plan (device side, no host round trip): thresholds well above the uniform-case bucket size
     {
         const uint64_t avg = n / plan.nb + 1, total = (uint64_t)plan.nwin * n;
-        out->heavy_t = (uint32_t)(16 * avg > HEAVY_CHUNK ? (16 * avg < 0xFFFFFFFFull ? 16 * avg : 0xFFFFFFFFull) : HEAVY_CHUNK);
+        // The top window of a 254-bit scalar has only 254 - c*(nwin-1) bits: its buckets are 2^(c-1) / 2^topbits times fuller than
+        // the others (32x at c = 20: ~4096 references at n = 2^26) and still far too many for one CTA each, so the threshold sits
+        // above them (2 * HEAVY_CHUNK - 2 = SIZE_BINS - 2, which also keeps every light bucket in an exact population bin).
+        out->heavy_t = (uint32_t)(16 * avg > SIZE_BINS - 2 ? (16 * avg < 0xFFFFFFFFull ? 16 * avg : 0xFFFFFFFFull) : SIZE_BINS - 2);
         out->max_bkts = (uint32_t)(total / out->heavy_t + 1);
         out->max_blks = (uint32_t)(total / HEAVY_CHUNK + out->max_bkts);
         const size_t b_blk = (size_t)out->max_blks * sizeof(HeavyBlk), b_bkt = (size_t)out->max_bkts * sizeof(HeavyBkt);
@@ -324,13 +326,13 @@ int32_t msm_sort(zkpor_ctx *ctx, const void *d_scalars, uint64_t n, uint32_t fla
     }
     // bucket schedule: slots in order of decreasing population
     {
-        ZK_TRY(ctx->order.reserve(slots * 4 + 2 * SIZE_BINS * 4));
-        uint32_t *order = ctx->order.as<uint32_t>(), *hist = order + slots, *cursor = hist + SIZE_BINS;
+        ZK_TRY(ctx->order.reserve(slots * 4 + 3 * SIZE_BINS * 4));
+        uint32_t *order = ctx->order.as<uint32_t>(), *hist = order + slots, *cursor = hist + SIZE_BINS, *bin_start = cursor + SIZE_BINS;
         ZK_CUDA(cudaMemsetAsync(hist, 0, SIZE_BINS * 4, ctx->stream));
         ZK_LAUNCH(ctx, k_size_hist, 4 * ctx->sm_count, 256, 0, ctx->bucket_cnt.as<uint32_t>(), slots, hist);
-        ZK_LAUNCH(ctx, k_size_scan, 1, 256, 0, (const uint32_t *)hist, cursor);
+        ZK_LAUNCH(ctx, k_size_scan, 1, 256, 0, (const uint32_t *)hist, cursor, bin_start);
         ZK_LAUNCH(ctx, k_size_scatter, grid_for(slots, 256), 256, 0, ctx->bucket_cnt.as<uint32_t>(), slots, cursor, order);
-        out->order = order;
+        out->order = order; out->hist = hist; out->bin_start = bin_start;
     }
     stage_end(ctx, ST_SORT);
     out->plan = plan; out->n = n;
@@ -346,8 +348,12 @@ static int32_t msm_accumulate(zkpor_ctx *ctx, const void *d_points, const MsmSor
     stage_begin(ctx, ST_ACCUM);
     {
         KTimed kt(ctx, sizeof(F) == sizeof(Fp) ? KC_ACCUM_G1 : KC_ACCUM_G2, s.n);
-        ZK_LAUNCH(ctx, (k_accumulate<F>), grid_for(slots, 128), 128, 0, (const Affine<F> *)d_points, s.idx, s.off, s.cnt, s.n, plan, s.heavy_t,
-                  s.order, ctx->buckets.as<XYZZ<F>>());
+        // light buckets: batched-affine tree rounds + XYZZ tail (msm_affine.cu) when the lists are long enough, else XYZZ only
+        bool done = false;
+        ZK_TRY(msm_tree_sums(ctx, (const Affine<F> *)d_points, s, ctx->buckets.as<XYZZ<F>>(), &done));
+        if (!done)
+            ZK_LAUNCH(ctx, (k_accumulate<F>), grid_for(slots, 128), 128, 0, (const Affine<F> *)d_points, s.idx, s.off, s.cnt, s.n, plan, s.heavy_t,
+                      s.order, ctx->buckets.as<XYZZ<F>>());
         ZK_TRY(ctx->heavy_part.reserve((size_t)s.max_blks * sizeof(XYZZ<F>)));
         ZK_LAUNCH(ctx, (k_accumulate_heavy<F>), (s.max_blks < 8u * ctx->sm_count ? s.max_blks : 8u * ctx->sm_count), 128, 0, (const Affine<F> *)d_points, s.idx, s.blks, s.counters, s.n, plan,
                   ctx->heavy_part.as<XYZZ<F>>());
