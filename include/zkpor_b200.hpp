@@ -148,6 +148,34 @@ inline std::vector<uint8_t> Prove(Context &ctx, ProvingKey &pk, const void *wire
     out.resize(n);
     return out;
 }
+// groth16.Verify (src/prover/prover/prover.go:276, src/verifier/main.go:284): true = valid; a malformed proof throws.
+// public_witness: n_public Montgomery fr.Elements, without the ONE wire.
+inline bool Verify(Context &ctx, const zkpor_vk_desc &vk, const std::vector<uint8_t> &proof_raw, const void *public_witness, uint64_t n_public) {
+    int32_t ok = 0;
+    check(zkpor_groth16_verify(ctx.get(), &vk, proof_raw.data(), (uint32_t)proof_raw.size(), public_witness, n_public, &ok));
+    return ok != 0;
+}
+// every proof of one circuit with a single pairing product (the verifier service's loop, src/verifier/main.go:176-302)
+inline bool VerifyBatch(Context &ctx, const zkpor_vk_desc &vk, const std::vector<std::vector<uint8_t>> &proofs, const void *public_witnesses,
+                        uint64_t n_public, const Hash &seed) {
+    if (proofs.empty()) return true;
+    const size_t len = proofs[0].size();
+    std::vector<uint8_t> flat(len * proofs.size());
+    for (size_t i = 0; i < proofs.size(); i++) {
+        if (proofs[i].size() != len) throw Error("zkpor: proofs of one batch must have one length");
+        std::copy(proofs[i].begin(), proofs[i].end(), flat.begin() + i * len);
+    }
+    int32_t ok = 0;
+    check(zkpor_groth16_verify_batch(ctx.get(), &vk, flat.data(), (uint32_t)len, len, public_witnesses, n_public, proofs.size(), seed.data(), &ok));
+    return ok != 0;
+}
 }  // namespace groth16
+
+// bn254.PairingCheck: prod e(P_i, Q_i) == 1
+inline bool PairingCheck(Context &ctx, const void *g1_points, const void *g2_points, uint64_t n) {
+    int32_t ok = 0;
+    check(zkpor_pairing_check(ctx.get(), g1_points, g2_points, n, &ok));
+    return ok != 0;
+}
 
 }  // namespace zkpor
