@@ -121,6 +121,23 @@ def test_heavy_buckets_skewed_witness(ctx):
     assert np.array_equal(ctx.msm_g2(p2, s2, n2), orc.g2_msm(p2, s2))
 
 
+def test_partitioned_sort_skewed_and_plain(ctx):
+    """n >= 2^18 takes the two-level (partitioned) counting sort: witness-like scalars (one bucket with ~15% of all terms, most
+    partitions nearly empty), canonical-integer input, and the largest canonical scalars (top window fully populated)."""
+    n = 300000
+    pts = g1_points(4096, 51); pts = np.ascontiguousarray(np.tile(pts, (n // 4096 + 1, 1))[:n])
+    ss = rand_scalars(n, 52, "witness")
+    ss[7] = R - 1; ss[8] = R - 2; ss[9] = (1 << 253) + 1; ss[10] = (1 << 240) - 1; ss[11] = 1 << 240
+    sc = orc.fr_mont(ss)
+    want = orc.g1_msm(pts, sc)
+    assert np.array_equal(ctx.msm_g1(pts, sc, n), want)
+    assert np.array_equal(ctx.msm_g1(pts, orc.ints_to_limbs(ss), n, zk.ZKPOR_SCALARS_PLAIN), want)
+    n2 = 1 << 18
+    p2 = g2_points(512, 53); p2 = np.ascontiguousarray(np.tile(p2, (n2 // 512, 1)))
+    s2 = rand_scalars_np(n2, 54)
+    assert np.array_equal(ctx.msm_g2(p2, s2, n2), orc.g2_msm(p2, s2))
+
+
 def test_device_pointer_inputs(ctx):
     import torch
     n = 5000

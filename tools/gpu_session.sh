@@ -1,7 +1,6 @@
 #!/bin/bash
-# development helper: one gpurun call = the whole GPU test suite, the contract benchmark and its ncu launch list
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/s_tests.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/s_tests.log
-timeout 900 python bench.py > gpurun_out/s_bench.json 2> gpurun_out/s_bench.err; echo "bench rc=$?"; cat gpurun_out/s_bench.json | cut -c1-1500; tail -3 gpurun_out/s_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_bench_logn22.csv python bench.py --steps 2 --warmup 1 --log-n 22 --no-e2e --no-cpu > gpurun_out/s_bench_ncu.log 2>&1; echo "ncu rc=$?"
+timeout 2400 python -m pytest tests/test_gpu_msm.py tests/test_gpu_groth16.py tests/test_gpu_fullsize.py -x -q > gpurun_out/s_tests.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/s_tests.log
+timeout 600 python tools/microbench.py msm check > gpurun_out/s_mb_part.log 2>&1; echo "mb partitioned rc=$?"; grep -E "msm_g|check" gpurun_out/s_mb_part.log
+timeout 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/probe_launches.csv python tools/affine_probe.py 26 > gpurun_out/probe.log 2>&1; tail -2 gpurun_out/probe.log

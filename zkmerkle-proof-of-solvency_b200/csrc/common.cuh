@@ -71,8 +71,9 @@ struct zkpor_ctx {
     uint64_t launches = 0;
     int poseidon_out_lane = 1;
     // scratch
-    zk::DevBuf in_points, in_scalars, sort_idx, bucket_cnt, bucket_off, bucket_cur, buckets, partials, windows, misc, ntt_a, ntt_b, ntt_c, io, heavy, heavy_part, order, tree_a, tree_b, tree_meta;
+    zk::DevBuf in_points, in_scalars, sort_idx, sort_idx2, view_cnt, view_order, part_buf, part_meta, bucket_cnt, bucket_off, bucket_cur, buckets, partials, windows, misc, ntt_a, ntt_b, ntt_c, io, heavy, heavy_part, order, tree_a, tree_b, tree_meta;
     bool g2_tight_regs = true;   // env ZKPOR_G2_TIGHT=0: G2 affine rounds at 170 registers / 8 warps per SM instead of 128 / 16
+    bool direct_scatter = false;   // env ZKPOR_DIRECT_SCATTER=1: one-level counting sort (returning L2 atomics) at every size
     int affine_rounds = 0;    // affine tree rounds of an MSM: 0 = XYZZ only (default), -1 = automatic depth, k > 0 = at most k; env ZKPOR_AFFINE_ROUNDS
     void *pinned = nullptr; size_t pinned_cap = 0;
     // poseidon constants on device (built lazily)

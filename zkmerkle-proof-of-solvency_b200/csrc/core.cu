@@ -76,6 +76,7 @@ int32_t zkpor_ctx_create(int32_t device_id, zkpor_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char *v = getenv("ZKPOR_AFFINE_ROUNDS")) ctx->affine_rounds = atoi(v);
     if (const char *v = getenv("ZKPOR_G2_TIGHT")) ctx->g2_tight_regs = atoi(v) != 0;
+    if (const char *v = getenv("ZKPOR_DIRECT_SCATTER")) ctx->direct_scatter = atoi(v) != 0;
     ZK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ZK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     ZK_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
@@ -95,7 +96,7 @@ int32_t zkpor_ctx_destroy(zkpor_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
-    zk::DevBuf *bufs[] = {&ctx->in_points, &ctx->in_scalars, &ctx->sort_idx, &ctx->bucket_cnt, &ctx->bucket_off, &ctx->bucket_cur,
+    zk::DevBuf *bufs[] = {&ctx->in_points, &ctx->in_scalars, &ctx->sort_idx, &ctx->sort_idx2, &ctx->view_cnt, &ctx->view_order, &ctx->part_buf, &ctx->part_meta, &ctx->bucket_cnt, &ctx->bucket_off, &ctx->bucket_cur,
                           &ctx->buckets, &ctx->partials, &ctx->windows, &ctx->misc, &ctx->ntt_a, &ctx->ntt_b, &ctx->ntt_c, &ctx->io, &ctx->heavy, &ctx->heavy_part, &ctx->order, &ctx->tree_a, &ctx->tree_b, &ctx->tree_meta};
     for (auto *b : bufs) b->release();
     zk_free_poseidon(ctx); zk_free_ntt(ctx);

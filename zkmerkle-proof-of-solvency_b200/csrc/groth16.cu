@@ -9,6 +9,8 @@
 //   Krs = MSM(K, wK) + MSM(Z, h[:n-1]) + (-r*s)*delta1 + s*Ar + r*Bs1
 // wA / wB drop the wires whose A / B query is the point at infinity (pk.InfinityA/B); wK drops the public wires, the
 // committed wires and the commitment wire.  Output = proof.WriteRawTo bytes.
+// A, B1, B2 and K multiply (subsets of) the SAME wire vector, so the digits and the counting sort by bucket are computed
+// once over all wires; each multiplication then takes its own view of the shared lists (msm_view: skip bitmap + rank map).
 #include "internal.h"
 
 using namespace ff;
@@ -19,7 +21,8 @@ struct zkpor_pk {
     uint64_t n_wires = 0, n_a = 0, n_b = 0, n_k = 0, n_z = 0, n_ck = 0;
     G1Affine *A = nullptr, *B1 = nullptr, *K = nullptr, *Z = nullptr, *ck = nullptr, *ck_sigma = nullptr;
     G2Affine *B2 = nullptr;
-    uint32_t *idx_a = nullptr, *idx_b = nullptr, *idx_k = nullptr, *idx_c = nullptr;   // gather indices into the wire vector
+    uint32_t *idx_c = nullptr;                                     // gather indices of the committed wires
+    uint2 *map_a = nullptr, *map_b = nullptr, *map_k = nullptr;   // wire -> key-point maps of the shared sort (msm.cu map_wire)
     G1Affine alpha1, beta1, delta1;
     G2Affine beta2, delta2;
     bool has_commitment = false;
@@ -83,7 +86,7 @@ extern "C" {
 int32_t zkpor_pk_free(zkpor_ctx *ctx, zkpor_pk *pk) {
     (void)ctx;
     if (!pk) return ZKPOR_OK;
-    void *ptrs[] = {pk->A, pk->B1, pk->K, pk->Z, pk->ck, pk->ck_sigma, pk->B2, pk->idx_a, pk->idx_b, pk->idx_k, pk->idx_c};
+    void *ptrs[] = {pk->A, pk->B1, pk->K, pk->Z, pk->ck, pk->ck_sigma, pk->B2, pk->idx_c, pk->map_a, pk->map_b, pk->map_k};
     for (void *p : ptrs) if (p) cudaFree(p);
     pk->wires.release(); pk->sub.release();
     delete pk;
@@ -111,7 +114,7 @@ int32_t zkpor_pk_upload(zkpor_ctx *ctx, const zkpor_pk_desc *d, zkpor_pk **out) 
     if (rc == ZKPOR_OK && d->n_wires > 0) {
         if (!d->infinity_a || !d->infinity_b) { set_error("pk_upload: infinity maps missing"); rc = ZKPOR_ERR_INVALID_ARG; }
         else {
-            std::vector<uint32_t> ia, ib, ik, ic;
+            std::vector<uint32_t> ic;
             std::vector<uint8_t> drop(d->n_wires, 0);
             for (uint64_t i = 0; i < d->n_committed; i++) {
                 if (d->private_committed[i] >= d->n_wires) { set_error("pk_upload: committed wire out of range"); rc = ZKPOR_ERR_INVALID_ARG; break; }
@@ -122,19 +125,31 @@ int32_t zkpor_pk_upload(zkpor_ctx *ctx, const zkpor_pk_desc *d, zkpor_pk **out) 
                 else drop[d->commitment_index] = 1;
             }
             if (rc == ZKPOR_OK) {
-                for (uint64_t i = 0; i < d->n_wires; i++) {
-                    if (!d->infinity_a[i]) ia.push_back((uint32_t)i);
-                    if (!d->infinity_b[i]) ib.push_back((uint32_t)i);
-                    if (i >= d->n_public && !drop[i]) ik.push_back((uint32_t)i);
+                // per 32 wires: skip bits and the rank (index in the compact key array) of the first wire of the word
+                const uint64_t words = (d->n_wires + 31) / 32;
+                std::vector<uint2> ma(words), mb(words), mk(words);
+                uint32_t ra = 0, rb = 0, rk = 0;
+                for (uint64_t w = 0; w < words; w++) {
+                    uint32_t ba = 0, bb = 0, bk = 0;
+                    for (uint32_t j = 0; j < 32; j++) {
+                        const uint64_t i = w * 32 + j;
+                        const bool in = i < d->n_wires;
+                        if (!in || d->infinity_a[i]) ba |= 1u << j;
+                        if (!in || d->infinity_b[i]) bb |= 1u << j;
+                        if (!in || i < d->n_public || drop[i]) bk |= 1u << j;
+                    }
+                    ma[w] = make_uint2(ba, ra); mb[w] = make_uint2(bb, rb); mk[w] = make_uint2(bk, rk);
+                    ra += 32 - __builtin_popcount(ba); rb += 32 - __builtin_popcount(bb); rk += 32 - __builtin_popcount(bk);
                 }
-                if (ia.size() != d->n_a || ib.size() != d->n_b || ik.size() != d->n_k) {
-                    set_error("pk_upload: key sizes inconsistent with infinity/commitment maps (A %zu/%llu, B %zu/%llu, K %zu/%llu)", ia.size(),
-                              (unsigned long long)d->n_a, ib.size(), (unsigned long long)d->n_b, ik.size(), (unsigned long long)d->n_k);
+                if (ra != d->n_a || rb != d->n_b || rk != d->n_k) {
+                    set_error("pk_upload: key sizes inconsistent with infinity/commitment maps (A %u/%llu, B %u/%llu, K %u/%llu)", ra,
+                              (unsigned long long)d->n_a, rb, (unsigned long long)d->n_b, rk, (unsigned long long)d->n_k);
                     rc = ZKPOR_ERR_INVALID_ARG;
                 }
+                up((void **)&pk->map_a, ma.data(), words * sizeof(uint2)); up((void **)&pk->map_b, mb.data(), words * sizeof(uint2));
+                up((void **)&pk->map_k, mk.data(), words * sizeof(uint2));
             }
-            up((void **)&pk->idx_a, ia.data(), ia.size() * 4); up((void **)&pk->idx_b, ib.data(), ib.size() * 4);
-            up((void **)&pk->idx_k, ik.data(), ik.size() * 4); up((void **)&pk->idx_c, ic.data(), ic.size() * 4);
+            up((void **)&pk->idx_c, ic.data(), ic.size() * 4);
         }
     }
     if (rc == ZKPOR_OK && d->n_z != (1ull << d->log_n) - 1 && d->n_wires > 0) { set_error("pk_upload: len(Z) must be 2^log_n - 1"); rc = ZKPOR_ERR_INVALID_ARG; }
@@ -181,8 +196,7 @@ int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, con
     }
     ZK_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
 
-    uint64_t max_sub = pk->n_a; if (pk->n_b > max_sub) max_sub = pk->n_b; if (pk->n_k > max_sub) max_sub = pk->n_k; if (pk->n_ck > max_sub) max_sub = pk->n_ck;
-    ZK_TRY(pk->sub.reserve((max_sub ? max_sub : 1) * 32));
+    ZK_TRY(pk->sub.reserve((pk->n_ck ? pk->n_ck : 1) * 32));
     Fr *sub = pk->sub.as<Fr>();
     ProofParts pp;
     pp.commit = G1XYZZ::inf(); pp.pok = G1XYZZ::inf();
@@ -194,19 +208,21 @@ int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, con
         ZK_TRY(msm_accumulate_g1(ctx, pk->ck_sigma, srt, &pp.pok));
     }
     pp.ar = G1XYZZ::inf(); pp.bs1 = G1XYZZ::inf(); pp.bs2 = G2XYZZ::inf(); pp.krs_k = G1XYZZ::inf(); pp.krs_z = G1XYZZ::inf();
+    // one digit extraction + counting sort over the whole wire vector, four accumulations through their wire maps
+    ZK_TRY(msm_sort(ctx, dw, pk->n_wires, ZKPOR_SCALARS_MONT, &srt));
+    MsmSorted view;
     if (pk->n_a) {
-        ZK_LAUNCH(ctx, k_gather_fr, grid_for(pk->n_a, 256), 256, 0, (const Fr *)dw, (const uint32_t *)pk->idx_a, pk->n_a, sub);
-        ZK_TRY(msm_g1_dev(ctx, pk->A, sub, pk->n_a, ZKPOR_SCALARS_MONT, &pp.ar));
+        ZK_TRY(msm_view(ctx, srt, pk->map_a, &view));
+        ZK_TRY(msm_accumulate_g1(ctx, pk->A, view, &pp.ar, pk->n_a));
     }
     if (pk->n_b) {
-        ZK_LAUNCH(ctx, k_gather_fr, grid_for(pk->n_b, 256), 256, 0, (const Fr *)dw, (const uint32_t *)pk->idx_b, pk->n_b, sub);
-        ZK_TRY(msm_sort(ctx, sub, pk->n_b, ZKPOR_SCALARS_MONT, &srt));      // one sort, two accumulations (G1 and G2)
-        ZK_TRY(msm_accumulate_g1(ctx, pk->B1, srt, &pp.bs1));
-        ZK_TRY(msm_accumulate_g2(ctx, pk->B2, srt, &pp.bs2));
+        ZK_TRY(msm_view(ctx, srt, pk->map_b, &view));      // one view, two accumulations (G1 and G2)
+        ZK_TRY(msm_accumulate_g1(ctx, pk->B1, view, &pp.bs1, pk->n_b));
+        ZK_TRY(msm_accumulate_g2(ctx, pk->B2, view, &pp.bs2, pk->n_b));
     }
     if (pk->n_k) {
-        ZK_LAUNCH(ctx, k_gather_fr, grid_for(pk->n_k, 256), 256, 0, (const Fr *)dw, (const uint32_t *)pk->idx_k, pk->n_k, sub);
-        ZK_TRY(msm_g1_dev(ctx, pk->K, sub, pk->n_k, ZKPOR_SCALARS_MONT, &pp.krs_k));
+        ZK_TRY(msm_view(ctx, srt, pk->map_k, &view));
+        ZK_TRY(msm_accumulate_g1(ctx, pk->K, view, &pp.krs_k, pk->n_k));
     }
     ZK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
     ZK_TRY(compute_h_dev(ctx, dst[0], dst[1], dst[2], pk->log_n));

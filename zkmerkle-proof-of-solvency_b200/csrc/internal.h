@@ -18,15 +18,23 @@ struct HeavyBkt { uint32_t slot, first_blk, nblk; };
 // Population bins of the bucket schedule: slots (window, bucket) are ordered by decreasing reference count with a counting
 // sort over SIZE_BINS exact bins (heavy buckets, > heavy_t <= SIZE_BINS - 2 references, share the last bin).
 static const uint32_t SIZE_BINS = 8192;
+static const uint32_t HEAVY_CHUNK = 4096;        // references per CTA of the heavy-bucket path
+static const uint32_t REF_SKIP = 0xFFFFFFFFu;    // entry of a view's heavy list that is not part of the multiplication
 struct MsmSorted {
     MsmPlan plan; uint64_t n; const uint32_t *idx, *off, *cnt, *order;   // order: slots by decreasing population
     const uint32_t *hist, *bin_start;   // slots per population bin; first position of a bin in `order`
+    bool is_view = false;               // a multiplication's view of a shared sort (msm_view)
     uint32_t heavy_t, max_blks, max_bkts; const HeavyBlk *blks; const HeavyBkt *bkts; const uint32_t *counters;
 };
 
 int32_t msm_sort(zkpor_ctx *ctx, const void *d_scalars, uint64_t n, uint32_t flags, MsmSorted *out);
-int32_t msm_accumulate_g1(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, ec::G1XYZZ *host_out);
-int32_t msm_accumulate_g2(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, ec::G2XYZZ *host_out);
+// `terms` = points actually added (length of the compact key array when s is a view), for the per-launch kernel statistics
+int32_t msm_accumulate_g1(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, ec::G1XYZZ *host_out, uint64_t terms = 0);
+int32_t msm_accumulate_g2(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, ec::G2XYZZ *host_out, uint64_t terms = 0);
+// One multiplication's view of a sort that ran over a whole wire vector shared by several multiplications: word w of the map =
+// {skip bits of wires 32w..32w+31, rank of wire 32w in the compact key array} (zkpor_pk_upload in groth16.cu).  The view lives in
+// ctx scratch until the next msm_view / msm_sort.
+int32_t msm_view(zkpor_ctx *ctx, const MsmSorted &shared, const uint2 *wire_map, MsmSorted *view);
 // sums of the light buckets (cnt <= heavy_t) by batched-affine tree rounds + an XYZZ tail (msm_affine.cu); *done = false
 // when the lists are too short for it to pay (or HBM is short) and the caller must run the XYZZ accumulation instead
 int32_t msm_tree_sums(zkpor_ctx *ctx, const ec::G1Affine *d_points, const MsmSorted &s, ec::G1XYZZ *buckets, bool *done);
