@@ -242,6 +242,8 @@ def main():
         return 0
     if args.impl == "reference":
         os.environ.pop("OMP_NUM_THREADS", None)   # torchrun pins it to 1; the CPU arm uses every host core
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout otherwise; stdout carries ONE JSON line
     import torch
     import zkpor_b200 as zk
     if not torch.cuda.is_available():
