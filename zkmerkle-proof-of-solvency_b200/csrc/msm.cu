@@ -28,8 +28,11 @@ template <class F> __device__ __forceinline__ Affine<F> load_affine(const Affine
     return r;
 }
 
+#ifndef ZK_G2_ACC_MINB
+#define ZK_G2_ACC_MINB 1
+#endif
 template <class F>
-__global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict__ points, const uint32_t *__restrict__ sorted,
+__global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fp) ? 1 : ZK_G2_ACC_MINB) k_accumulate(const Affine<F> *__restrict__ points, const uint32_t *__restrict__ sorted,
                                                     const uint32_t *__restrict__ off, const uint32_t *__restrict__ cnt,
                                                     uint64_t n, MsmPlan plan, uint32_t heavy_t, const uint32_t *__restrict__ order,
                                                     XYZZ<F> *__restrict__ buckets) {
