@@ -140,6 +140,28 @@ int32_t zkpor_groth16_finish(const void *partials /* k x ZKPOR_PROVE_PARTIAL_BYT
                              const uint8_t r_be[32], const uint8_t s_be[32], int32_t has_commitment, uint8_t *out_proof,
                              uint32_t *out_len);
 
+/* ---- constraint evaluation (the linear-algebra half of r1cs.Solve) ----------------------------------
+ * gnark's solver fills solution.A/B/C with <L_k, w>, <R_k, w>, <O_k, w> for every constraint k while it solves
+ * (constraint/bn254/solver.go, out of tree; reached from groth16.Prove, src/prover/prover/prover.go:269).  With the three
+ * matrices resident in HBM the Go side hands over the wire vector only: 2.1 GB per 2^26 proof instead of 8.4 GB.
+ * Matrices are compressed sparse rows as gnark stores linear expressions: per term a wire id and an id into the shared
+ * coefficient table (constraint.CoeffTable: Montgomery fr.Elements). */
+typedef struct zkpor_r1cs zkpor_r1cs;
+typedef struct {
+    uint64_t nnz;
+    const uint64_t *row_ptr;      /* n_constraints + 1 entries */
+    const uint32_t *wire_ids;     /* nnz */
+    const uint32_t *coeff_ids;    /* nnz */
+} zkpor_csr;
+int32_t zkpor_r1cs_upload(zkpor_ctx *ctx, uint64_t n_constraints, uint64_t n_wires, const zkpor_csr *l, const zkpor_csr *r,
+                          const zkpor_csr *o, const void *coeff_table /* n_coeffs x 32 B */, uint64_t n_coeffs, zkpor_r1cs **out);
+int32_t zkpor_r1cs_free(zkpor_ctx *ctx, zkpor_r1cs *cs);
+/* a = L w, b = R w, c = O w (n_constraints Montgomery elements each; host or device outputs) */
+int32_t zkpor_r1cs_eval(zkpor_ctx *ctx, zkpor_r1cs *cs, const void *wires, void *out_a, void *out_b, void *out_c);
+/* zkpor_groth16_prove with a, b, c evaluated on the device from the wire vector */
+int32_t zkpor_groth16_prove_wires(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, const void *wires, const uint8_t r_be[32],
+                                  const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len);
+
 /* ---- pairing / groth16.Verify --------------------------------------------------------------
  * Replaces gnark-crypto bn254.MillerLoop / FinalExponentiation / PairingCheck (ecc/bn254/pairing.go, out of tree) under
  * groth16.Verify -- src/prover/prover/prover.go:276, src/verifier/main.go:284.  Miller loops run one pair per GPU thread;

@@ -111,3 +111,20 @@ def make_pk(zk, ctx, inst):
                          infinity_a=sc["infinity_a"], infinity_b=sc["infinity_b"], n_public=cs.nb_public,
                          ck_basis=arr["ck_basis"], ck_basis_exp_sigma=arr["ck_basis_exp_sigma"],
                          private_committed=cs.private_committed, commitment_index=cs.commitment_index)
+
+
+def r1cs_csr(cs):
+    """CSR matrices + coefficient table of an oracle R1CS in the layout zkpor_b200.R1CS takes (ids 0..4 = 0, 1, 2, -1, -2 as in gnark's table)"""
+    table = [0, 1, 2, R - 1, R - 2]
+    ids = {v: i for i, v in enumerate(table)}
+    mats = []
+    for rows in (cs.L, cs.Rr, cs.O):
+        rp, wi, ci = [0], [], []
+        for terms in rows:
+            for cf, w in terms:
+                if cf not in ids:
+                    ids[cf] = len(table); table.append(cf)
+                wi.append(w); ci.append(ids[cf])
+            rp.append(len(wi))
+        mats.append((np.array(rp, dtype=np.uint64), np.array(wi, dtype=np.uint32), np.array(ci, dtype=np.uint32)))
+    return mats, orc.fr_mont(table)

@@ -7,7 +7,7 @@ import groth16 as g16
 import orc
 import zkpor_b200 as zk
 from bn254 import R, SplitMix64
-from helpers import H, golden, make_pk, oracle_proof, synthetic_instance
+from helpers import H, golden, make_pk, oracle_proof, r1cs_csr, synthetic_instance
 from test_oracle_c import pk_arrays_from_golden
 
 pytestmark = pytest.mark.gpu
@@ -72,4 +72,58 @@ def test_synthetic_prove_vs_oracle(ctx, n_constraints, nb_secret):
                                        len(range(*sl(hz).indices(nz)))))
         key.close()
     assert pk.finish(np.stack(parts), r, s) == want
+    pk.close()
+
+
+def test_constraint_evaluation_and_prove_from_wires(ctx):
+    """a = L w, b = R w, c = O w on the device (the linear-algebra half of r1cs.Solve) bit-exact against the oracle's solver, and
+    groth16.Prove from the wire vector alone gives the same proof bytes as with a, b, c handed over."""
+    n_constraints = 900
+    inst = synthetic_instance(n_constraints, 60, seed=31)
+    cs = inst["cs"]
+    mats, table = r1cs_csr(cs)
+    r1 = zk.R1CS(ctx, n_constraints, cs.nb_wires, mats, table)
+    m = orc.fr_mont
+    a, b, c = r1.eval(m(inst["w"]))
+    assert orc.fr_unmont(a) == inst["a"] and orc.fr_unmont(b) == inst["b"]
+    assert orc.fr_unmont(c) == [x * y % R for x, y in zip(inst["a"], inst["b"])] == inst["c"]
+    import torch
+    dw = torch.from_numpy(m(inst["w"]).view(np.int64)).cuda()
+    a2, _, _ = r1.eval(dw)                                   # device-resident wires
+    assert np.array_equal(a, a2)
+    rng = SplitMix64(32)
+    r, s = rng.field(R), rng.field(R)
+    pk = make_pk(zk, ctx, inst)
+    want = oracle_proof(inst, r, s)
+    assert pk.prove_wires(r1, m(inst["w"]), r, s) == want
+    assert pk.prove(m(inst["w"]), m(inst["a"]), m(inst["b"]), m(inst["c"]), n_constraints, r, s) == want
+    # malformed matrices are rejected on upload
+    bad = [(mats[0][0], mats[0][1].copy(), mats[0][2]), mats[1], mats[2]]
+    bad[0][1][0] = cs.nb_wires
+    with pytest.raises(zk.ZkporError):
+        zk.R1CS(ctx, n_constraints, cs.nb_wires, bad, table)
+    pk.close(); r1.close()
+
+
+def test_prove_and_verify_without_commitment(ctx):
+    """circuit without a BSB22 commitment: 324-byte proof (zero CommitmentPok), vk without a Pedersen key"""
+    import groth16 as g
+    from helpers import pk_arrays
+    cs = g.synth_r1cs(300, 20, seed=41, with_commitment=False)
+    tox = g.toxic_from_seed(42)
+    sc = g.setup_scalars(cs, tox)
+    arr = pk_arrays(sc, tox)
+    pub, sec = g.synth_inputs(cs, 43)
+    w, a, b, c, _, _ = g.solve(cs, None, pub, sec)
+    pk = zk.ProvingKey(ctx, log_n=arr["log_n"], A=arr["A"], B1=arr["B1"], K=arr["K"], Z=arr["Z"], B2=arr["B2"],
+                       alpha1=arr["alpha1"], beta1=arr["beta1"], delta1=arr["delta1"], beta2=arr["beta2"], delta2=arr["delta2"],
+                       n_a=len(sc["A_s"]), n_b=len(sc["B_s"]), n_k=len(sc["K_s"]), n_z=len(sc["Z_s"]),
+                       infinity_a=sc["infinity_a"], infinity_b=sc["infinity_b"], n_public=cs.nb_public)
+    m = orc.fr_mont
+    proof = pk.prove(m(w), m(a), m(b), m(c), 300, 0x1234, 0x5678)
+    assert len(proof) == 324
+    from helpers import oracle_vk, vk_arrays
+    vk = zk.VerifyingKey(**vk_arrays(dict(vk=oracle_vk(cs, sc, tox))))
+    assert vk.verify(ctx, proof, m(pub))
+    assert not vk.verify(ctx, proof, m([(pub[0] + 1) % R]))
     pk.close()

@@ -460,6 +460,15 @@ class ProvingKey:
                                          _ptr(out), C.byref(n)))
         return out[:n.value].tobytes()
 
+    def prove_wires(self, cs: "R1CS", wires, r: int, s: int) -> bytes:
+        """groth16.Prove from the wire vector alone: a, b, c = L w, R w, O w are evaluated on the device (R1CS resident in HBM)."""
+        out = np.zeros(388, dtype=np.uint8)
+        n = C.c_uint32(0)
+        rb = (C.c_uint8 * 32).from_buffer_copy(be32(r % R_MOD))
+        sb = (C.c_uint8 * 32).from_buffer_copy(be32(s % R_MOD))
+        _check(lib().zkpor_groth16_prove_wires(self.ctx._h, self._h, cs._h, _ptr(wires), rb, sb, _ptr(out), C.byref(n)))
+        return out[:n.value].tobytes()
+
     def prove_partial(self, wires_a, wires_b, wires_k, committed, h_chunk, n_h: int) -> np.ndarray:
         out = np.zeros(PROVE_PARTIAL_BYTES, dtype=np.uint8)
         _check(lib().zkpor_groth16_prove_partial(self.ctx._h, self._h, _ptr(wires_a), _ptr(wires_b), _ptr(wires_k), _ptr(committed),
@@ -556,6 +565,46 @@ def groth16_setup(ctx: Context, log_n: int, n_wires: int, nb_public: int, csc_a,
         pk_kwargs.update(ck_basis=fb(ck_s), ck_basis_exp_sigma=fb(ck_sigma_s), private_committed=committed.astype(np.uint64), commitment_index=commitment_index)
     extras = dict(vk_K=fb(vk_s), gamma2=one(toxic["gamma"], True), n_vk=int(vk_s.shape[0]))
     return pk_kwargs, extras
+
+
+# ----------------------------------------------------------------------------------------------- constraint evaluation
+class Csr(C.Structure):
+    _fields_ = [("nnz", C.c_uint64), ("row_ptr", C.c_void_p), ("wire_ids", C.c_void_p), ("coeff_ids", C.c_void_p)]
+
+
+class R1CS:
+    """The three R1CS matrices resident in HBM (what r1cs.ReadFrom fills at prover.go:317-327, flattened to CSR by the shim):
+    matrices = [(row_ptr u64[n+1], wire_ids u32[nnz], coeff_ids u32[nnz])] * 3 for L, R, O; coeff_table = (k, 4) u64 Montgomery."""
+
+    def __init__(self, ctx: Context, n_constraints: int, n_wires: int, matrices, coeff_table):
+        self.ctx = ctx
+        self.n_constraints = n_constraints
+        keep, descs = [], []
+        for row_ptr, wire_ids, coeff_ids in matrices:
+            rp = np.ascontiguousarray(row_ptr, dtype=np.uint64); wi = np.ascontiguousarray(wire_ids, dtype=np.uint32); ci = np.ascontiguousarray(coeff_ids, dtype=np.uint32)
+            keep += [rp, wi, ci]
+            descs.append(Csr(wi.size, _ptr(rp), _ptr(wi) if wi.size else None, _ptr(ci) if ci.size else None))
+        tab = np.ascontiguousarray(coeff_table, dtype=np.uint64).reshape(-1, 4)
+        self._h = C.c_void_p()
+        _check(lib().zkpor_r1cs_upload(ctx._h, C.c_uint64(n_constraints), C.c_uint64(n_wires), C.byref(descs[0]), C.byref(descs[1]), C.byref(descs[2]),
+                                       _ptr(tab), C.c_uint64(tab.shape[0]), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().zkpor_r1cs_free(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def eval(self, wires):
+        """(a, b, c) = (L w, R w, O w) as (n_constraints, 4) uint64 Montgomery arrays"""
+        outs = [np.zeros((self.n_constraints, 4), dtype=np.uint64) for _ in range(3)]
+        _check(lib().zkpor_r1cs_eval(self.ctx._h, self._h, _ptr(wires), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2])))
+        return outs
 
 
 # ----------------------------------------------------------------------------------------------- pairing / Verify

@@ -171,9 +171,9 @@ int32_t zkpor_pk_commit(zkpor_ctx *ctx, zkpor_pk *pk, const void *committed_valu
     return ZKPOR_OK;
 }
 
-int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, const void *a, const void *b, const void *c,
-                            uint64_t n_constraints, const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
-    ZK_REQUIRE(ctx && pk && wires && a && b && c && r_be && s_be && out_proof && out_len, "prove: null argument");
+// shared body of zkpor_groth16_prove (a, b, c from the caller) and zkpor_groth16_prove_wires (a, b, c = L w, R w, O w on the device)
+static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, const void *wires, const void *a, const void *b, const void *c,
+                          uint64_t n_constraints, const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
     ZK_REQUIRE(pk->n_wires > 0, "prove: key was uploaded without wire maps (sharded key?)");
     const size_t n = (size_t)1 << pk->log_n;
     ZK_REQUIRE(n_constraints > 0 && n_constraints <= n, "prove: n_constraints exceeds the domain");
@@ -190,9 +190,15 @@ int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, con
     const void *src[3] = {a, b, c};
     Fr *dst[3] = {ctx->ntt_a.as<Fr>(), ctx->ntt_b.as<Fr>(), ctx->ntt_c.as<Fr>()};
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));   // the previous call's use of the NTT buffers is over
-    for (int k = 0; k < 3; k++) {
-        ZK_CUDA(cudaMemcpyAsync(dst[k], src[k], in_bytes, cudaMemcpyDefault, ctx->copy_stream));
-        if (bytes > in_bytes) ZK_CUDA(cudaMemsetAsync((uint8_t *)dst[k] + in_bytes, 0, bytes - in_bytes, ctx->copy_stream));
+    if (cs != nullptr) {
+        // constraint evaluation on the device: needs only the wires, runs ahead of the multiplications on the compute stream
+        for (int k = 0; k < 3; k++) if (bytes > in_bytes) ZK_CUDA(cudaMemsetAsync((uint8_t *)dst[k] + in_bytes, 0, bytes - in_bytes, ctx->stream));
+        ZK_TRY(r1cs_eval_dev(ctx, cs, (const Fr *)dw, dst[0], dst[1], dst[2]));
+    } else {
+        for (int k = 0; k < 3; k++) {
+            ZK_CUDA(cudaMemcpyAsync(dst[k], src[k], in_bytes, cudaMemcpyDefault, ctx->copy_stream));
+            if (bytes > in_bytes) ZK_CUDA(cudaMemsetAsync((uint8_t *)dst[k] + in_bytes, 0, bytes - in_bytes, ctx->copy_stream));
+        }
     }
     ZK_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
 
@@ -230,6 +236,19 @@ int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, con
     assemble_proof(pp, pk->alpha1, pk->beta1, pk->delta1, pk->beta2, pk->delta2, r_be, s_be, pk->has_commitment, out_proof, out_len);
     stages_collect(ctx);
     return ZKPOR_OK;
+}
+
+int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, const void *a, const void *b, const void *c,
+                            uint64_t n_constraints, const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
+    ZK_REQUIRE(ctx && pk && wires && a && b && c && r_be && s_be && out_proof && out_len, "prove: null argument");
+    return prove_impl(ctx, pk, nullptr, wires, a, b, c, n_constraints, r_be, s_be, out_proof, out_len);
+}
+
+int32_t zkpor_groth16_prove_wires(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, const void *wires, const uint8_t r_be[32], const uint8_t s_be[32],
+                                  uint8_t *out_proof, uint32_t *out_len) {
+    ZK_REQUIRE(ctx && pk && cs && wires && r_be && s_be && out_proof && out_len, "prove_wires: null argument");
+    ZK_REQUIRE(r1cs_wires(cs) == pk->n_wires, "prove_wires: the constraint system and the key disagree on the number of wires");
+    return prove_impl(ctx, pk, cs, wires, nullptr, nullptr, nullptr, r1cs_rows(cs), r_be, s_be, out_proof, out_len);
 }
 
 int32_t zkpor_groth16_prove_partial(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires_a, const void *wires_b, const void *wires_k,

@@ -43,6 +43,11 @@ int32_t msm_tree_sums(zkpor_ctx *ctx, const ec::G2Affine *d_points, const MsmSor
 int32_t msm_g1_dev(zkpor_ctx *ctx, const void *d_points, const void *d_scalars, uint64_t n, uint32_t flags, ec::G1XYZZ *host_out);
 int32_t msm_g2_dev(zkpor_ctx *ctx, const void *d_points, const void *d_scalars, uint64_t n, uint32_t flags, ec::G2XYZZ *host_out);
 
+// R1CS matrices resident in HBM (r1cs.cu); out_* are device vectors of n_constraints elements
+int32_t r1cs_eval_dev(zkpor_ctx *ctx, zkpor_r1cs *cs, const ff::Fr *d_wires, ff::Fr *d_a, ff::Fr *d_b, ff::Fr *d_c);
+uint64_t r1cs_rows(const zkpor_r1cs *cs);
+uint64_t r1cs_wires(const zkpor_r1cs *cs);
+
 // NTT (device-resident data)
 int32_t ntt_dev(zkpor_ctx *ctx, ff::Fr *d_data, uint32_t log_n, bool inverse, bool dit, bool coset);
 int32_t compute_h_dev(zkpor_ctx *ctx, ff::Fr *d_a, ff::Fr *d_b, ff::Fr *d_c, uint32_t log_n);   // result in d_a (bit-reversed)
