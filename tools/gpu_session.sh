@@ -1,11 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 1200 python -m pytest tests/test_gpu_groth16.py tests/test_gpu_verify.py -x -q > gpurun_out/s_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/s_tests.log
-for ov in 0 1; do
-ZKPOR_OVERLAP_NTT=$ov timeout 900 python bench.py --no-cpu > gpurun_out/s_bench_ov$ov.json 2> gpurun_out/s_bench_ov$ov.err; echo "bench overlap=$ov rc=$?"; python - <<PY
-import json
-d=json.loads([l for l in open('gpurun_out/s_bench_ov$ov.json') if l.startswith('{')][-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['kernel_breakdown'], d['roofline']['launch_ms'], d['proof_sha'])
-PY
-done
+timeout 900 python bench.py > gpurun_out/s_bench.json 2> gpurun_out/s_bench.err; echo "bench rc=$?"; tail -c 600 gpurun_out/s_bench.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_bench_logn22_v4.csv python bench.py --steps 2 --warmup 1 --log-n 22 --no-e2e --no-cpu > gpurun_out/s_bench_ncu.log 2>&1; echo "ncu list rc=$?"
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"k_accumulate<|k_part_sort|k_view_lists" -s 2 -c 6 -o gpurun_out/r01_v4_kernels -f python bench.py --steps 1 --warmup 0 --log-n 24 --no-e2e --no-cpu > gpurun_out/s_bench_ncu2.log 2>&1; echo "ncu full rc=$?"
+timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/s_bench_ref.json 2> gpurun_out/s_bench_ref.err; echo "ref rc=$?"; tail -c 400 gpurun_out/s_bench_ref.json
