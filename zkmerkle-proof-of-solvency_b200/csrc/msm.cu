@@ -8,7 +8,7 @@
 //   3. k_scan           exclusive scan of the histogram per window
 //   4. k_digits<SCATTER> signed point references scattered to their bucket segment   (32 B read + 4*nwin B write)
 //   5. k_accumulate     one thread per (window, bucket): XYZZ += affine point, gathered 64/128 B loads
-//   6. k_reduce_seg / k_sum_groups   sum_b b*B_b per window by segmented running sums
+//   6. k_reduce_level   sum_b b*B_b per window by a tree of short running sums (8 buckets per thread and level)
 //   7. host             Horner over the nwin window sums (nwin*c doublings) -- O(1) work, 2 KB copied back
 // The result of an MSM is a group element, so any bucket order gives bit-identical affine output.
 #include "internal.h"
@@ -119,33 +119,30 @@ __global__ void __launch_bounds__(128) k_heavy_combine(const XYZZ<F> *__restrict
     }
 }
 
-// thread (w, seg): sum_{j in seg} (j+1) * B[w][j]  via running sums, segment length L
+// Bucket reduction W = sum_j (j+1) X_j of every window, as a tree of short running sums (no scalar multiplications):
+// split X into segments of L: (i+1) = L g + (t+1), so W(X) = sum_g S_g + L (W(R) - T) with S_g = sum_t (t+1) X_{Lg+t},
+// R_g = sum_t X_{Lg+t}, T = the total.  Recursing on R until one element (= T) is left gives
+//     W = sum_l L^l U_l  -  T (L + L^2 + ... + L^(K-1)),      U_l = sum_g S^l_g,   K levels.
+// Level l: thread (w, g) walks its <= L elements once from the top -- run += X, sum += run (2 additions per element) -- and
+// also sums the carried array A^l (the descendants' sum_{j<l} L^j S^j), writing R_g and A^{l+1}_g = sum A^l + L^l S^l_g.  After
+// the last level A = sum_l L^l U_l and R = T; the host subtracts the multiple of T.  Chains are L additions long (the
+// previous scheme: 64 + a 19-bit scalar multiplication per thread, a quarter as many threads).
 template <class F>
-__global__ void __launch_bounds__(128) k_reduce_seg(const XYZZ<F> *__restrict__ buckets, MsmPlan plan, uint32_t L, uint32_t segs,
-                                                    XYZZ<F> *__restrict__ partials) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= plan.nwin * segs) return;
-    uint32_t w = t / segs, seg = t % segs;
-    uint32_t lo = seg * L, hi = min(lo + L, plan.nb);
-    const XYZZ<F> *B = buckets + (size_t)w * plan.nb;
+__global__ void __launch_bounds__(128) k_reduce_level(const XYZZ<F> *__restrict__ X, const XYZZ<F> *__restrict__ A, uint32_t m_in, uint32_t m_out,
+                                                      uint32_t L, uint32_t dbl, uint32_t nwin, XYZZ<F> *__restrict__ R, XYZZ<F> *__restrict__ An) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nwin * m_out) return;
+    const uint32_t w = t / m_out, g = t - w * m_out;
+    const uint32_t lo = g * L, hi = min(lo + L, m_in);
+    const XYZZ<F> *x = X + (size_t)w * m_in;
     XYZZ<F> run = XYZZ<F>::inf(), sum = XYZZ<F>::inf();
-    for (uint32_t j = hi; j-- > lo;) { run.add(B[j]); sum.add(run); }
-    // sum = sum_j (j - lo + 1) B_j ; add lo * run
-    if (lo) sum.add(run.mul_u32(lo));
-    partials[t] = sum;
-}
-
-// out[w*groups_out + g] = sum_{k < group} in[w*count_in + g*group + k]
-template <class F>
-__global__ void __launch_bounds__(128) k_sum_groups(const XYZZ<F> *__restrict__ in, uint32_t count_in, uint32_t group, uint32_t groups_out,
-                                                    uint32_t nwin, XYZZ<F> *__restrict__ out) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nwin * groups_out) return;
-    uint32_t w = t / groups_out, g = t % groups_out;
-    uint32_t lo = g * group, hi = min(lo + group, count_in);
-    XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = lo; k < hi; k++) acc.add(in[(size_t)w * count_in + k]);
-    out[t] = acc;
+    for (uint32_t j = hi; j-- > lo;) { run.add(x[j]); sum.add(run); }
+    for (uint32_t k = 0; k < dbl; k++) sum = sum.dbl();       // L^l S
+    if (A != nullptr) {
+        const XYZZ<F> *a = A + (size_t)w * m_in;
+        for (uint32_t j = lo; j < hi; j++) sum.add(a[j]);
+    }
+    R[t] = run; An[t] = sum;
 }
 
 template <class F>
@@ -171,27 +168,46 @@ static int32_t msm_accumulate(zkpor_ctx *ctx, const void *d_points, const MsmSor
     }
     stage_end(ctx, ST_ACCUM);
     stage_begin(ctx, ST_REDUCE);
-    const uint32_t L = plan.nb >= 32 ? 32 : plan.nb;
-    uint32_t count = (plan.nb + L - 1) / L;
-    ZK_TRY(ctx->partials.reserve((size_t)plan.nwin * count * sizeof(XYZZ<F>) * 2));
-    XYZZ<F> *cur = ctx->partials.as<XYZZ<F>>(), *nxt = cur + (size_t)plan.nwin * count;
-    ZK_LAUNCH(ctx, (k_reduce_seg<F>), grid_for((size_t)plan.nwin * count, 128), 128, 0, ctx->buckets.as<XYZZ<F>>(), plan, L, count, cur);
-    while (count > 1) {
-        uint32_t groups = (count + 31) / 32;
-        ZK_LAUNCH(ctx, (k_sum_groups<F>), grid_for((size_t)plan.nwin * groups, 128), 128, 0, cur, count, 32u, groups, plan.nwin, nxt);
-        XYZZ<F> *t = cur; cur = nxt; nxt = t; count = groups;
+    const uint32_t LOG_L = 3, L = 1u << LOG_L;
+    // level sizes nb -> ceil(nb/L) -> ... -> 1; R^l and A^{l+1} of every level live side by side in `partials`
+    uint32_t sizes[40], K = 0;
+    sizes[0] = plan.nb;
+    while (sizes[K] > 1) { sizes[K + 1] = (sizes[K] + L - 1) / L; K++; }
+    size_t total_out = 0;
+    for (uint32_t l = 1; l <= K; l++) total_out += sizes[l];
+    ZK_TRY(ctx->partials.reserve((total_out ? total_out : 1) * plan.nwin * sizeof(XYZZ<F>) * 2));
+    const XYZZ<F> *X = ctx->buckets.as<XYZZ<F>>(), *A = nullptr;
+    XYZZ<F> *out = ctx->partials.as<XYZZ<F>>();
+    for (uint32_t l = 0; l < K; l++) {
+        const size_t cnt_out = (size_t)plan.nwin * sizes[l + 1];
+        XYZZ<F> *R = out, *An = out + cnt_out;
+        ZK_LAUNCH(ctx, (k_reduce_level<F>), grid_for(cnt_out, 128), 128, 0, X, A, sizes[l], sizes[l + 1], L, l * LOG_L, plan.nwin, R, An);
+        X = R; A = An; out += 2 * cnt_out;
     }
     stage_end(ctx, ST_REDUCE);
-    // window sums -> host, Horner
-    std::vector<XYZZ<F>> ws(plan.nwin);
+    // per window (T, sum_l L^l U_l) -> host; W = that sum - T (L + ... + L^(K-1)); Horner over the windows
+    std::vector<XYZZ<F>> ws(2 * (size_t)plan.nwin);
     stage_begin(ctx, ST_D2H);
-    ZK_CUDA(cudaMemcpyAsync(ws.data(), cur, plan.nwin * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, ctx->stream));
+    if (K == 0) {   // one bucket per window: W = X
+        ZK_CUDA(cudaMemcpyAsync(ws.data(), X, plan.nwin * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        ZK_CUDA(cudaMemcpyAsync(ws.data(), X, plan.nwin * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, ctx->stream));                 // T per window
+        ZK_CUDA(cudaMemcpyAsync(ws.data() + plan.nwin, A, plan.nwin * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, ctx->stream));    // sum_l L^l U_l
+    }
     stage_end(ctx, ST_D2H);
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
-    XYZZ<F> acc = ws[plan.nwin - 1];
+    uint32_t cmul = 0;
+    for (uint32_t l = 1; l < K; l++) cmul += 1u << (l * LOG_L);
+    auto window_sum = [&](uint32_t w) {
+        if (K == 0) return ws[w];
+        XYZZ<F> r = ws[plan.nwin + w];
+        if (cmul) r.add(ws[w].mul_u32(cmul).negated());
+        return r;
+    };
+    XYZZ<F> acc = window_sum(plan.nwin - 1);
     for (int w = (int)plan.nwin - 2; w >= 0; w--) {
         for (uint32_t k = 0; k < plan.c; k++) acc = acc.dbl();
-        acc.add(ws[w]);
+        acc.add(window_sum((uint32_t)w));
     }
     *host_out = acc;
     return ZKPOR_OK;
