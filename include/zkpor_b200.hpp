@@ -148,6 +148,24 @@ inline std::vector<uint8_t> Prove(Context &ctx, ProvingKey &pk, const void *wire
     out.resize(n);
     return out;
 }
+// R1CS matrices resident in HBM + groth16.Prove from the wire vector alone (a, b, c evaluated on the device)
+class R1cs {
+  public:
+    R1cs(Context &ctx, uint64_t n_constraints, uint64_t n_wires, const zkpor_csr &l, const zkpor_csr &r, const zkpor_csr &o, const void *coeff_table,
+         uint64_t n_coeffs) : ctx_(ctx) { check(zkpor_r1cs_upload(ctx.get(), n_constraints, n_wires, &l, &r, &o, coeff_table, n_coeffs, &h_)); }
+    ~R1cs() { zkpor_r1cs_free(ctx_.get(), h_); }
+    R1cs(const R1cs &) = delete;
+    zkpor_r1cs *get() const { return h_; }
+    void Eval(const void *wires, void *a, void *b, void *c) { check(zkpor_r1cs_eval(ctx_.get(), h_, wires, a, b, c)); }
+  private:
+    Context &ctx_; zkpor_r1cs *h_ = nullptr;
+};
+inline std::vector<uint8_t> ProveWires(Context &ctx, ProvingKey &pk, R1cs &cs, const void *wires, const Hash &r, const Hash &s) {
+    std::vector<uint8_t> out(388); uint32_t n = 0;
+    check(zkpor_groth16_prove_wires(ctx.get(), pk.get(), cs.get(), wires, r.data(), s.data(), out.data(), &n));
+    out.resize(n);
+    return out;
+}
 // groth16.Verify (src/prover/prover/prover.go:276, src/verifier/main.go:284): true = valid; a malformed proof throws.
 // public_witness: n_public Montgomery fr.Elements, without the ONE wire.
 inline bool Verify(Context &ctx, const zkpor_vk_desc &vk, const std::vector<uint8_t> &proof_raw, const void *public_witness, uint64_t n_public) {
