@@ -1,7 +1,8 @@
 #!/bin/bash
+# Development helper: what one `gpurun -- bash tools/gpu_session.sh` call runs.  EVERY step has its own short timeout: a kernel
+# that hangs must cost a minute, not the round's GPU budget (it did once: profiles/r01_SUMMARY.md, "two lanes per G2 bucket").
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 1200 python -m pytest tests/test_gpu_msm.py tests/test_gpu_groth16.py tests/test_gpu_verify.py -x -q > gpurun_out/s_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/s_tests.log
-for v in 0 4 3 2; do
-ZKPOR_G2_PAIR=$v timeout 600 python tools/microbench.py g2 > gpurun_out/s_mb_pair$v.log 2>&1; echo "pair=$v rc=$?"; grep -E "msm_g2" gpurun_out/s_mb_pair$v.log
-done
+timeout 180 python -m pytest tests -m gpu -x -q > gpurun_out/s_tests.log 2>&1; rc=$?; echo "tests rc=$rc"; tail -4 gpurun_out/s_tests.log
+[ $rc -ne 0 ] && exit $rc        # nothing else is queued behind a failing or hanging test run
+timeout 240 python bench.py --no-cpu > gpurun_out/s_bench.json 2> gpurun_out/s_bench.err; echo "bench rc=$?"; tail -c 400 gpurun_out/s_bench.json
