@@ -13,6 +13,7 @@
 // STATUS: experimental, NOT validated on a GPU yet (opt-in through ZKPOR_G2_PAIR; see g2_pair_lanes in msm.cu).
 // Same reference seam as msm.cu: gnark-crypto G2Jac.MultiExp inside groth16.Prove (src/prover/prover/prover.go:269).
 #include "internal.h"
+#include "fp2_split.cuh"
 #include <cstdlib>
 
 using namespace ff;
@@ -22,59 +23,27 @@ namespace zk {
 
 namespace {
 
-__device__ __forceinline__ Fp xchg(uint32_t mask, const Fp &v) {
-    Fp r;
+// device lane pair: role = lane & 1, exchange = 8 shuffles with the partner lane; `mask` names the lanes that execute the call
+struct LanePair {
+    uint32_t mask; bool role;
+    __device__ __forceinline__ Fp xchg(const Fp &v) const {
+        Fp r;
 #pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(mask, v.l[i], 1);
-    return r;
-}
-__device__ __forceinline__ Fp sel(bool c, const Fp &a, const Fp &b) {   // c ? a : b without a branch
-    Fp r;
+        for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(mask, v.l[i], 1);
+        return r;
+    }
+    __device__ __forceinline__ Fp sel_role(const Fp &a, const Fp &b) const {   // role ? a : b without a branch
+        Fp r;
 #pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = c ? a.l[i] : b.l[i];
-    return r;
-}
-__device__ __forceinline__ bool pair_zero(uint32_t mask, const Fp &v) {
-    const int z = v.is_zero();
-    return z & __shfl_xor_sync(mask, z, 1);
-}
-// z = x*y, t = u*v (split Fp2 values; role = lane & 1)
-__device__ __forceinline__ void mul2(uint32_t mask, bool role, const Fp &x, const Fp &y, const Fp &u, const Fp &v, Fp &z, Fp &t) {
-    // lane0 needs (x1, y1) for its Karatsuba middle term, lane1 needs (u0, v0)
-    const Fp r1 = xchg(mask, sel(role, x, u)), r2 = xchg(mask, sel(role, y, v));
-    const Fp own1 = Fp::mul(x, y);                                   // lane0: A = x0 y0      lane1: C = x1 y1
-    const Fp own2 = Fp::mul(u, v);                                   // lane0: B = u0 v0      lane1: D = u1 v1
-    const Fp m = Fp::mul(Fp::add(sel(role, u, x), r1), Fp::add(sel(role, v, y), r2));   // lane0: M1, lane1: M2
-    const Fp e1 = xchg(mask, sel(role, own1, Fp::sub(m, own1)));     // lane0 receives C      lane1 receives M1 - A
-    const Fp e2 = xchg(mask, own2);                                  // lane0 receives D      lane1 receives B
-    // lane0: z0 = A - C, t0 = B - D        lane1: z1 = (M1 - A) - C, t1 = M2 - B - D
-    z = sel(role, Fp::sub(e1, own1), Fp::sub(own1, e1));
-    t = sel(role, Fp::sub(Fp::sub(m, e2), own2), Fp::sub(own2, e2));
-}
-__device__ __forceinline__ Fp sqr(uint32_t mask, bool role, const Fp &a) {
-    const Fp ao = xchg(mask, a);
-    const Fp r = Fp::mul(sel(role, a, Fp::add(a, ao)), sel(role, ao, Fp::sub(a, ao)));   // lane0: (a0+a1)(a0-a1), lane1: a1 a0
-    return sel(role, Fp::dbl(r), r);
-}
-
-struct SplitAcc { Fp X, Y, ZZ, ZZZ; };
-
-// 2 * (px, py) in XYZZ form (mdbl-2008-s), split
-__device__ __forceinline__ SplitAcc dbl_affine_split(uint32_t mask, bool role, const Fp &px, const Fp &py) {
-    const Fp U = Fp::dbl(py);
-    const Fp V = sqr(mask, role, U);
-    Fp W, S;
-    mul2(mask, role, U, V, px, V, W, S);
-    const Fp xx = sqr(mask, role, px);
-    const Fp M = Fp::add(Fp::dbl(xx), xx);
-    SplitAcc r;
-    r.X = Fp::sub(sqr(mask, role, M), Fp::dbl(S));
-    Fp t1, t2;
-    mul2(mask, role, M, Fp::sub(S, r.X), W, py, t1, t2);
-    r.Y = Fp::sub(t1, t2);
-    r.ZZ = V; r.ZZZ = W;
-    return r;
-}
+        for (int i = 0; i < 8; i++) r.l[i] = role ? a.l[i] : b.l[i];
+        return r;
+    }
+    __device__ __forceinline__ bool pair_zero(const Fp &v) const {             // both components zero (every lane of `mask` must call this)
+        const int z = v.is_zero();
+        return z & __shfl_xor_sync(mask, z, 1);
+    }
+};
+using SplitAcc = fp2split::Acc<Fp>;
 
 __device__ __forceinline__ Fp load_fp(const Fp *p) {
     Fp r;
@@ -121,41 +90,31 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate_g2_pair(const G2Affine
     uint32_t e = m ? __ldg(idx) : 0;
     Fp px = Fp::zero(), py = Fp::zero();
     if (m) load_pt(e, px, py);
+    const LanePair ln{FULL, role};
     for (uint32_t k = 0; k < steps; k++) {
         const bool active = k < m;
         // next reference and point in flight while this one is added
         uint32_t en = 0; Fp nx = px, ny = py;
         if (k + 1 < m) { en = __ldg(idx + k + 1); load_pt(en, nx, ny); }
-        const bool p_inf = pair_zero(FULL, px) & pair_zero(FULL, py);
+        // NOTE: everything that shuffles (pair_zero, madd, ...) is evaluated by EVERY lane before it is combined with lane-dependent
+        // conditions: a shuffle behind a short-circuited `&&` deadlocked the first version of this kernel
+        const bool px_zero = ln.pair_zero(px), py_zero = ln.pair_zero(py);
+        const bool p_inf = px_zero & py_zero;
         const Fp y2 = (e & 1) ? Fp::neg(py) : py;
-        // madd-2008-s on split values (computed unconditionally; special cases select afterwards)
-        Fp U2, S2;
-        mul2(FULL, role, px, acc.ZZ, y2, acc.ZZZ, U2, S2);
-        const Fp P = Fp::sub(U2, acc.X), R = Fp::sub(S2, acc.Y);
-        const Fp PP = sqr(FULL, role, P);
-        Fp PPP, Q;
-        mul2(FULL, role, P, PP, acc.X, PP, PPP, Q);
-        const Fp X3 = Fp::sub(Fp::sub(sqr(FULL, role, R), PPP), Fp::dbl(Q));
-        Fp t1, t2;
-        mul2(FULL, role, R, Fp::sub(Q, X3), acc.Y, PPP, t1, t2);
-        Fp ZZ3, ZZZ3;
-        mul2(FULL, role, acc.ZZ, PP, acc.ZZZ, PPP, ZZ3, ZZZ3);
-        SplitAcc nxt;
-        nxt.X = X3; nxt.Y = Fp::sub(t1, t2); nxt.ZZ = ZZ3; nxt.ZZZ = ZZZ3;
+        // madd-2008-s on split values (fp2_split.cuh; computed unconditionally, special cases are selected afterwards)
+        Fp P, R;
+        SplitAcc nxt = fp2split::madd(ln, acc, px, y2, P, R);
+        const bool p_zero = ln.pair_zero(P), r_zero = ln.pair_zero(R);
         bool nxt_inf = false;
         // same x: doubling (same y) or cancellation -- rare, pair-uniform; the lanes concerned are named by a ballot
-        // NOTE: the shuffles inside pair_zero must be reached by every lane: evaluate them BEFORE combining with lane-dependent
-        // conditions (the first version wrote `active && ... && pair_zero(FULL, P)`; the short circuit skipped the shuffle on
-        // some lanes and the warp deadlocked)
-        const bool p_zero = pair_zero(FULL, P);
-        const bool same_y = pair_zero(FULL, R);
-        const bool same_x = active && !p_inf && !acc_inf && p_zero;
-        const uint32_t dmask = __ballot_sync(FULL, same_x && same_y);
-        if (same_x && same_y) nxt = dbl_affine_split(dmask, role, px, y2);
-        if (same_x && !same_y) nxt_inf = true;
+        const bool same_x = active & !p_inf & !acc_inf & p_zero;
+        const bool need_dbl = same_x & r_zero;
+        const uint32_t dmask = __ballot_sync(FULL, need_dbl);
+        if (need_dbl) nxt = fp2split::dbl_affine(LanePair{dmask, role}, px, y2);
+        if (same_x & !r_zero) nxt_inf = true;
         // first point of the list: the accumulator becomes the point
         if (acc_inf) { nxt.X = px; nxt.Y = y2; nxt.ZZ = one_split; nxt.ZZZ = one_split; nxt_inf = false; }
-        if (active && !p_inf) {
+        if (active & !p_inf) {
             acc = nxt; acc_inf = nxt_inf;
             if (nxt_inf) { acc.X = one_split; acc.Y = one_split; acc.ZZ = Fp::zero(); acc.ZZZ = Fp::zero(); }
         }
