@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(128) k_reduce_level(const XYZZ<F> *__restrict_
 }
 
 // ZKPOR_G2_PAIR=2|3|4 (resident CTAs per SM): a lane pair per G2 bucket (msm_g2pair.cu) instead of one thread per bucket.
-// OFF by default: the kernel is not validated yet -- its first version deadlocked on the GPU (a warp shuffle behind a
-// short-circuited condition) and the round's GPU budget ended with it; see DESIGN.md 6b.
+// OFF by default: correct (host-emulated formulas, oracle parity on the GPU) but measured 27 % slower than the kernel below
+// (DESIGN.md 6b).
 static bool g2_pair_lanes() {
     static const bool on = [] { const char *v = getenv("ZKPOR_G2_PAIR"); return v != nullptr && atoi(v) >= 2; }();
     return on;

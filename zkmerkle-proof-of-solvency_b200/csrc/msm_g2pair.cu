@@ -10,7 +10,8 @@
 //                     (u0+u1)(v0+v1) -- three products per lane, four 8-word exchanges (operands, then M1-A / C and B / D)
 // The mixed addition madd-2008-s is exactly four independent product pairs and two squarings: 14 products per lane = the 28
 // base-field products of the one-thread form, no extra multiplications.
-// STATUS: experimental, NOT validated on a GPU yet (opt-in through ZKPOR_G2_PAIR; see g2_pair_lanes in msm.cu).
+// STATUS: opt-in (ZKPOR_G2_PAIR; see g2_pair_lanes in msm.cu): gives the oracle's result, but measured 27 % slower than one thread
+// per bucket (2^22 terms: 44 ms vs 35 ms) -- the unconditional special-case arithmetic and the spills cost more than the occupancy gains.
 // Same reference seam as msm.cu: gnark-crypto G2Jac.MultiExp inside groth16.Prove (src/prover/prover/prover.go:269).
 #include "internal.h"
 #include "fp2_split.cuh"
