@@ -4,9 +4,12 @@
 // groth16.Prove -- src/prover/prover/prover.go:269.  Pipeline (all on ctx->stream, points/scalars resident in HBM):
 // (steps 1-4, the scalar side, live in msm_sort.cu)
 //   1. k_from_mont      scalars Montgomery -> canonical                              (streaming, 64 B/term)
-//   2. k_digits<HIST>   c-bit signed digits of every scalar, histogram per (window, bucket)   (32 B/term read)
-//   3. k_scan           exclusive scan of the histogram per window
-//   4. k_digits<SCATTER> signed point references scattered to their bucket segment   (32 B read + 4*nwin B write)
+//   2-4. counting sort of the signed point references (index << 1 | sign) by (window, bucket):
+//        n <  2^18: k_digits<HIST> (RED histogram), k_scan, k_digits<SCATTER> (one returning L2 atomic per term and window)
+//        n >= 2^18: k_part_count / k_part_scan / k_part_scatter / k_part_sort -- 64 partitions per window, counters and
+//                   cursors in shared memory
+//        then the heavy-bucket plan and the population schedule (slots by decreasing reference count); for a sort shared
+//        by several multiplications (groth16.cu) msm_view derives each multiplication's lists from it
 //   5. k_accumulate     one thread per (window, bucket): XYZZ += affine point, gathered 64/128 B loads
 //   6. k_reduce_level   sum_b b*B_b per window by a tree of short running sums (8 buckets per thread and level)
 //   7. host             Horner over the nwin window sums (nwin*c doublings) -- O(1) work, 2 KB copied back
