@@ -28,6 +28,25 @@ def test_library_exports_every_declared_symbol():
     assert [lib.zkpor_stage_name(i).decode() for i in range(3)] == ["h2d", "digits", "sort"]
 
 
+def test_header_is_plain_c():
+    """the boundary is a C ABI: the header must compile as C11 (cgo includes it as such)"""
+    import subprocess
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "zkpor_b200.h")])
+
+
+def test_null_arguments_of_the_newer_entry_points():
+    lib = zk.lib()
+    for call in (lambda: lib.zkpor_pairing_check(None, None, None, 0, None),
+                 lambda: lib.zkpor_groth16_verify(None, None, None, 0, None, 0, None),
+                 lambda: lib.zkpor_groth16_verify_batch(None, None, None, 0, 0, None, 0, 0, None, None),
+                 lambda: lib.zkpor_r1cs_upload(None, 0, 0, None, None, None, None, 0, None),
+                 lambda: lib.zkpor_r1cs_eval(None, None, None, None, None, None),
+                 lambda: lib.zkpor_groth16_prove_wires(None, None, None, None, None, None, None, None),
+                 lambda: lib.zkpor_msm_set_affine_rounds(None, 0)):
+        assert call() == 1                              # ZKPOR_ERR_INVALID_ARG, never a crash
+        assert lib.zkpor_last_error()
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
