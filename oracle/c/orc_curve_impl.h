@@ -134,8 +134,10 @@ static void CV(msm)(CV(jac) *out, const CV(aff) *pts, const uint64_t *sc /* plai
     int c = 4;
     { size_t t = n; int lg = 0; while (t >>= 1) lg++; c = lg <= 6 ? 3 : lg <= 10 ? 6 : lg <= 14 ? 10 : lg <= 18 ? 12 : lg <= 22 ? 14 : 16; }
     int nw = (254 + c - 1) / c;
+    /* tasks = windows x point chunks: about three tasks per thread keep a dynamic schedule balanced (19 windows on 16 threads
+       with one chunk each would leave most threads idle for half of the time) */
     int chunks = 1;
-    if (threads > nw && n >= (1u << 14)) chunks = (threads + nw - 1) / nw;
+    if (threads > 1 && n >= (1u << 14)) chunks = (3 * threads + nw - 1) / nw;
     size_t per = (n + chunks - 1) / chunks;
     int ntask = nw * chunks;
     CV(jac) *part = (CV(jac) *)malloc(sizeof(CV(jac)) * ntask);
