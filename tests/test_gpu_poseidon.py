@@ -32,6 +32,30 @@ def test_reference_fixture_chain_on_gpu(ctx):
         assert ctx.poseidon_bytes(pr[i], pr[i]) == pr[i + 1]
 
 
+def test_reference_fixture_wide_sponge_on_gpu(ctx):
+    """The fixture's empty-subtree chain from its nil leaf: Poseidon(0,0,0,0, Poseidon(0 x 584)) hashed up 15 levels = proof[15]
+    (test_oracle_kat.py::test_reference_fixture_pins_wide_sponge_and_leaf_hash) -- the wide sponge, the width-6 leaf hash and the
+    node hash of the CUDA path against the reference's own bytes, no oracle involved."""
+    fx = json.load(open(os.path.join(GOLDEN, "user_config_proof.json")))
+    pr = [base64.b64decode(x) for x in fx["Proof"]]
+    ctx.set_poseidon_out_lane(1)
+    z = bytes(32)
+    empty_assets = ctx.poseidon_hash_batch(np.zeros(584 * 32, dtype=np.uint8), 584, 1).tobytes()
+    v = ctx.poseidon_bytes(z, z, z, z, empty_assets)
+    for _ in range(15):
+        v = ctx.poseidon_bytes(v, v)
+    assert v == pr[15]
+    # and through the tree itself: a depth-28 tree whose nil leaf is that hash has the fixture's empty-subtree siblings
+    nil_leaf = ctx.poseidon_bytes(z, z, z, z, empty_assets)
+    t = zk.FixedDepthMerkleTree(ctx, 28, nil_leaf, 4)
+    t.set_range(0, np.frombuffer(nil_leaf * 4, dtype=np.uint8), 4)
+    t.build()
+    proof = t.get_proofs(np.array([0], dtype=np.uint32)).reshape(28, 32)
+    for lvl in range(15, 28):
+        assert proof[lvl].tobytes() == pr[lvl]
+    t.close()
+
+
 def test_published_vectors_lane0(ctx):
     ctx.set_poseidon_out_lane(0)
     assert ctx.poseidon_bytes(b"\x01", b"\x02").hex() == "115cc0f5e7d690413df64c6b9662e9cf2a3617f2743245519e19607a4417189a"

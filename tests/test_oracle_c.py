@@ -138,3 +138,16 @@ def test_c_groth16_prove_bytes(vec):
                               orc.fr_mont(H(g["a"])), orc.fr_mont(H(g["b"])), orc.fr_mont(H(g["c"])),
                               int(g["r"], 16), int(g["s"], 16))
     assert proof.hex() == g["proof_raw"]
+
+
+def test_c_reference_fixture_wide_sponge():
+    """C oracle against the reference fixture: nil leaf of the fixture's circuit generation -> proof[15] (see test_oracle_kat.py)."""
+    import base64
+    fx = json.load(open(os.path.join(GOLDEN, "user_config_proof.json")))
+    pr = [int.from_bytes(base64.b64decode(x), "big") for x in fx["Proof"]]
+    orc.poseidon_set_out_lane(1)
+    hv = lambda xs: orc.fr_unmont(orc.poseidon_hash(orc.fr_mont(xs)))[0]
+    v = hv([0, 0, 0, 0, hv([0] * 584)])
+    for _ in range(15):
+        v = hv([v, v])
+    assert v == pr[15]

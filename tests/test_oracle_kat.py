@@ -47,6 +47,31 @@ def test_reference_fixture_node_hash_chain():
     assert ps.OUT_LANE == 1
 
 
+def test_reference_fixture_pins_wide_sponge_and_leaf_hash():
+    """The same fixture pins the WIDE sponge and the 5-input account hash: its empty-subtree chain starts from the nil leaf of the
+    circuit generation that produced it (350 assets x 5 uint64 fields, three per element -> 584 packed zero elements):
+        nil_leaf = Poseidon(0, 0, 0, 0, Poseidon(0 x 584));  proof[15] = H^15(nil_leaf)
+    584 = 48 x 12 + 8: forty-eight width-13 permutations chained through lane 0, a width-9 tail, a width-6 leaf hash and fifteen
+    width-3 node hashes, every output taken from lane 1.  Found by search over (element count, leaf arity, lanes); a 254-bit match is
+    conclusive.  This pins rows a8/a9 (AccountInfoToHash, the assets / CEX commitments) to the reference's bytes."""
+    fx = json.load(open(os.path.join(GOLDEN, "user_config_proof.json")))
+    pr = [int.from_bytes(base64.b64decode(x), "big") for x in fx["Proof"]]
+    assert ps.OUT_LANE == 1
+    empty_assets = ps.poseidon([0] * 584)
+    v = ps.poseidon([0, 0, 0, 0, empty_assets])
+    for _ in range(15):
+        v = ps.poseidon([v, v])
+    assert v == pr[15]
+    # neither lane 0 at the wide hash nor at the leaf reproduces it
+    for wide_lane, leaf_lane in ((0, 1), (1, 0), (0, 0)):
+        w = ps.poseidon([0, 0, 0, 0, ps.poseidon([0] * 584, wide_lane)], leaf_lane)
+        for _ in range(15):
+            w = ps.poseidon([w, w])
+        assert w != pr[15]
+    # today's nil leaf (src/utils/constants.go:125-127) goes through the same, now pinned, width-6 hash
+    assert merkle.nil_account_hash() == ps.poseidon([0, 0, 0, 0, 0]).to_bytes(32, "big")
+
+
 def test_hasher_wrapper_semantics():
     h = ps.PoseidonHasher()
     h.write(b"\x00")           # zero index encodes as []byte{0} (witness.go:185-192)
