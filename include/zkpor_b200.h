@@ -162,6 +162,58 @@ int32_t zkpor_r1cs_eval(zkpor_ctx *ctx, zkpor_r1cs *cs, const void *wires, void 
 int32_t zkpor_groth16_prove_wires(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, const void *wires, const uint8_t r_be[32],
                                   const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len);
 
+/* ---- witness solver (r1cs.Solve with its hints) --------------------------------------------------------
+ * Replaces gnark's constraint solver (constraint/bn254/solver.go + system.go, out of tree), the first step of groth16.Prove --
+ * src/prover/prover/prover.go:269 -- including the hint functions: the reference's own IntegerDivision (circuit/utils.go:103-110,
+ * registered at src/prover/prover/prover.go:68), gnark's std hints the circuit pulls in (bits.NBits behind api.ToBinary, InvZero
+ * behind api.IsZero, the rangecheck limb decomposition, the logderivlookup lookup and the logderivarg multiplicity count, the fork's
+ * CmpNOp comparator) and the BSB22 commitment placeholder that Prove overrides (solve -> Pedersen commit -> hash_to_field -> continue).
+ *
+ * The program is gnark's compiled constraint system flattened by the cgo shim (INTEGRATION.md "solver contract"):
+ *   - the three R1CS matrices + coefficient table (as zkpor_r1cs_upload),
+ *   - cs.Instructions as (kind, arg): kind R1C -> arg = constraint row; kind HINT -> arg = hint record,
+ *   - cs.Levels as level_ptr / level_instr (instruction ids; the instructions of one level are independent),
+ *   - hint records: function id, parameter, first output wire and number of outputs (gnark allocates a hint's outputs as
+ *     consecutive wires), and the inputs as rows [hint_in_ptr[h], hint_in_end[h]) of the auxiliary matrix `aux` of linear
+ *     expressions; lookup table t = rows [table_ptr[t], table_ptr[t+1]) of the same matrix.
+ * Which wire an R1C instruction solves for is not part of the contract: gnark finds it at run time (the one unsolved wire); this
+ * library finds it once, at upload, by a dry run of the schedule on the GPU. */
+#define ZKPOR_INS_R1C 0u
+#define ZKPOR_INS_HINT 1u
+#define ZKPOR_HINT_DIVMOD 1u      /* out = (in[0] / in[1], in[0] % in[1]) as integers: IntegerDivision, circuit/utils.go:103-110 */
+#define ZKPOR_HINT_NBITS 2u       /* out[i] = bit i of in[0]                                   (api.ToBinary)               */
+#define ZKPOR_HINT_INVZERO 3u     /* out = 1/in[0], or 0 when in[0] = 0                        (api.IsZero)                 */
+#define ZKPOR_HINT_DECOMPOSE 4u   /* out[i] = limb i of in[0], param bits per limb            (rangecheck.Check)           */
+#define ZKPOR_HINT_LOOKUP 5u      /* out[i] = table[param][in[i]]                              (logderivlookup.Lookup)      */
+#define ZKPOR_HINT_CMP 6u         /* out = -1 / 0 / 1 for in[0] <, =, > in[1] as integers      (api.CmpNOp)                 */
+#define ZKPOR_HINT_COUNT 7u       /* out[k] = #{i : in[i] = k}, k < n_out                      (logderivarg multiplicities) */
+#define ZKPOR_HINT_COMMIT 8u      /* out = hash_to_field(Pedersen commitment of pk's committed wires)  (BSB22 placeholder)  */
+typedef struct zkpor_program zkpor_program;
+typedef struct {
+    uint64_t n_wires, n_public /* includes the ONE wire */, n_secret, n_constraints;
+    zkpor_csr l, r, o;
+    const void *coeff_table; uint64_t n_coeffs;
+    uint64_t n_instr; const uint8_t *instr_kind; const uint32_t *instr_arg;
+    uint64_t n_levels; const uint64_t *level_ptr /* n_levels + 1 */; const uint32_t *level_instr /* n_instr */;
+    uint64_t n_hints; const uint32_t *hint_fn, *hint_param, *hint_out_first, *hint_n_out; const uint64_t *hint_in_ptr, *hint_in_end;
+    uint64_t n_aux_rows; zkpor_csr aux;
+    uint64_t n_tables; const uint64_t *table_ptr /* n_tables + 1 */;
+} zkpor_program_desc;
+int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *desc, zkpor_program **out);
+int32_t zkpor_program_free(zkpor_ctx *ctx, zkpor_program *prog);
+/* number of schedule steps by type: wide level launches, fused runs of narrow levels, levels inside those runs, count hints */
+int32_t zkpor_program_stats(zkpor_program *prog, uint64_t out4[4]);
+/* r1cs.Solve: inputs = the n_public - 1 public then the n_secret secret values (Montgomery).  out_wires = n_wires elements,
+ * out_a / out_b / out_c = n_constraints each (any of the four may be NULL).  pk supplies the commitment key and may be NULL for a
+ * program without a commitment hint; out_commitment64 (may be NULL) receives the commitment point.  An unsatisfied constraint,
+ * a division by zero or a lookup outside its table is ZKPOR_ERR_STATE with the first offending row in the message. */
+int32_t zkpor_r1cs_solve(zkpor_ctx *ctx, zkpor_program *prog, zkpor_pk *pk, const void *inputs, void *out_wires, void *out_a,
+                         void *out_b, void *out_c, void *out_commitment64);
+/* The whole of groth16.Prove (src/prover/prover/prover.go:269): solve, then the proof as zkpor_groth16_prove makes it.  The
+ * commitment and its proof of knowledge are computed once, mid-solve. */
+int32_t zkpor_groth16_prove_solve(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_program *prog, const void *inputs, const uint8_t r_be[32],
+                                  const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len);
+
 /* ---- pairing / groth16.Verify --------------------------------------------------------------
  * Replaces gnark-crypto bn254.MillerLoop / FinalExponentiation / PairingCheck (ecc/bn254/pairing.go, out of tree) under
  * groth16.Verify -- src/prover/prover/prover.go:276, src/verifier/main.go:284.  Miller loops run one pair per GPU thread;
@@ -202,6 +254,10 @@ int32_t zkpor_groth16_verify_batch(zkpor_ctx *ctx, const zkpor_vk_desc *vk, cons
  * sites src/utils/account_tree.go:19,27, src/utils/utils.go:748, src/witness/main.go:181) as batch calls. */
 /* output lane of the permutation (see DESIGN.md "Poseidon parity"): default 1 (the in-tree fixture), 0 = iden3 */
 int32_t zkpor_poseidon_set_out_lane(zkpor_ctx *ctx, int32_t lane);
+/* the permutation's parameters for width t = 2..13 as this library generates them (Grain LFSR, the iden3 / gnark-crypto fork set):
+ * (8 + rounds_p) * t round constants, t * t MDS entries (row-major), Montgomery fr.Elements, host buffers -- what the in-circuit
+ * gadget (gnark std/hash/poseidon, circuit/utils.go:19,48) must use to agree with the native hash */
+int32_t zkpor_poseidon_constants(uint32_t t, void *out_round_constants, void *out_mds, uint32_t *out_rounds_p);
 /* count independent hashes of n_in big-endian 32-byte elements each -> count x 32 B (PoseidonBytes semantics) */
 int32_t zkpor_poseidon_hash_batch(zkpor_ctx *ctx, const void *in_be, uint32_t n_in, uint64_t count, void *out_be);
 /* utils.AccountInfoToHash for a batch of accounts of one asset tier (src/utils/utils.go:744-750,188-221):

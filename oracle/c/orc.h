@@ -71,6 +71,33 @@ int orc_groth16_prove(const orc_pk *pk, const uint64_t *wires_a, const uint64_t 
                       const uint64_t *committed, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_constraints,
                       const uint64_t *r_plain, const uint64_t *s_plain, uint8_t *out_proof388, int threads);
 
+/* r1cs.Solve over the flat program arrays (orc_solver.c; same layout as zkpor_program_desc / circuit_synth.flatten()) */
+typedef struct {
+    uint64_t n_wires, n_public, n_secret, n_constraints;
+    const uint64_t *l_row_ptr; const uint32_t *l_wire, *l_coeff;
+    const uint64_t *r_row_ptr; const uint32_t *r_wire, *r_coeff;
+    const uint64_t *o_row_ptr; const uint32_t *o_wire, *o_coeff;
+    const uint64_t *coeffs; uint64_t n_coeffs;                       /* Montgomery */
+    uint64_t n_instr; const uint8_t *instr_kind; const uint32_t *instr_arg;
+    uint64_t n_levels; const uint64_t *level_ptr; const uint32_t *level_instr;
+    uint64_t n_hints; const uint32_t *hint_fn, *hint_param, *hint_out_first, *hint_n_out; const uint64_t *hint_in_ptr, *hint_in_end;
+    const uint64_t *aux_row_ptr; const uint32_t *aux_wire, *aux_coeff;
+    const uint64_t *table_ptr;
+    const uint64_t *private_committed; uint64_t n_committed;
+} orc_program;
+/* the overridden BSB22 hint: committed values (Montgomery) -> challenge (Montgomery) */
+typedef void (*orc_commit_fn)(const uint64_t *committed_mont, size_t n, uint64_t *challenge_mont, void *user);
+/* returns 0, or: 1 more than one unsolved wire, 2 division by zero, 3 index outside a table, 4 unknown hint, 5 hint reads an unsolved
+ * wire, 6 commitment hint without callback, 7 committed wire unsolved, 8 wire never solved, 9 constraint not satisfied (*err_at) */
+int orc_solve(const orc_program *p, const uint64_t *inputs_mont, uint64_t *wires_mont, uint64_t *a, uint64_t *b, uint64_t *c,
+              orc_commit_fn commit, void *user, uint64_t *err_at, int threads);
+void orc_commitment_challenge(const uint8_t *msg, size_t len, uint64_t *out_mont);
+/* the whole of groth16.Prove: solve (commitment mid-solve), filter the wires by infinity_a / infinity_b / public+committed, prove.
+ * seconds[0] = solver, seconds[1] = the rest */
+int orc_groth16_prove_program(const orc_pk *pk, const orc_program *prog, const uint8_t *infinity_a, const uint8_t *infinity_b,
+                              uint64_t commitment_index, const uint64_t *inputs_mont, const uint64_t *r_plain, const uint64_t *s_plain,
+                              uint8_t *out_proof388, double *seconds, uint64_t *err_at, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -176,9 +176,19 @@ void orc__g2_finish(uint8_t *o, const g2_jac *p) {
 /* ---- Groth16 prove: the group part (orc_groth16_prove lives here to reuse the static group law) ---- */
 void orc_compute_h(const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t m, int logn, uint64_t *out_h, int threads);
 
+static int prove_core(const orc_pk *pk, const uint64_t *wa, const uint64_t *wb, const uint64_t *wk, const uint64_t *committed,
+                      const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_constraints,
+                      const uint64_t *r_plain, const uint64_t *s_plain, uint8_t *out, int threads, const g1_jac *commit_done);
+
 int orc_groth16_prove(const orc_pk *pk, const uint64_t *wa, const uint64_t *wb, const uint64_t *wk, const uint64_t *committed,
                       const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_constraints,
                       const uint64_t *r_plain, const uint64_t *s_plain, uint8_t *out, int threads) {
+    return prove_core(pk, wa, wb, wk, committed, a, b, c, n_constraints, r_plain, s_plain, out, threads, NULL);
+}
+
+static int prove_core(const orc_pk *pk, const uint64_t *wa, const uint64_t *wb, const uint64_t *wk, const uint64_t *committed,
+                      const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_constraints,
+                      const uint64_t *r_plain, const uint64_t *s_plain, uint8_t *out, int threads, const g1_jac *commit_done) {
     /* Restates gnark v0.10 backend/groth16/bn254/prove.go after the solver has run:
      *   pok  = MSM(BasisExpSigma, committed)            commitment = MSM(Basis, committed)
      *   h    = computeH(a, b, c)                        (bit-reversed, paired with pk.G1.Z as stored)
@@ -193,7 +203,7 @@ int orc_groth16_prove(const orc_pk *pk, const uint64_t *wa, const uint64_t *wb, 
     orc_compute_h(a, b, c, n_constraints, pk->log_n, h, threads);
 
     g1_jac ar, bs1, krs, kz, t, commit, pok; g2_jac bs2, t2;
-    orc_g1_msm_jac(&commit, pk->ck_basis, committed, pk->n_ck, threads);
+    if (commit_done) commit = *commit_done; else orc_g1_msm_jac(&commit, pk->ck_basis, committed, pk->n_ck, threads);
     orc_g1_msm_jac(&pok, pk->ck_basis_exp_sigma, committed, pk->n_ck, threads);
     orc_g1_msm_jac(&ar, pk->A, wa, pk->n_a, threads);
     orc_g1_msm_jac(&bs1, pk->B1, wb, pk->n_b, threads);
@@ -221,4 +231,59 @@ int orc_groth16_prove(const orc_pk *pk, const uint64_t *wa, const uint64_t *wb, 
     out[256] = 0; out[257] = 0; out[258] = 0; out[259] = 1;
     orc__g1_finish(out + 260, &commit); orc__g1_finish(out + 324, &pok);
     return 0;
+}
+
+/* ---- groth16.Prove from the circuit inputs: solver (orc_solver.c) + the proof above ---------------------------------------- */
+typedef struct { const orc_pk *pk; g1_jac commit; uint64_t *committed; int threads; } commit_ctx;
+static void commit_cb(const uint64_t *vals, size_t n, uint64_t *challenge, void *user) {
+    commit_ctx *cc = (commit_ctx *)user;
+    uint8_t raw[64];
+    orc_g1_msm_jac(&cc->commit, cc->pk->ck_basis, vals, n, cc->threads);
+    orc__g1_finish(raw, &cc->commit);
+    cc->committed = (uint64_t *)malloc(32 * (n ? n : 1));
+    memcpy(cc->committed, vals, 32 * n);
+    orc_commitment_challenge(raw, 64, challenge);
+}
+/* keep[i] != 0 -> element i goes to the output, order preserved; parallel two-pass compaction */
+static size_t compact32(const uint64_t *src, size_t n, const uint8_t *keep, uint64_t *dst, int threads) {
+    const size_t nb = (size_t)threads * 8, per = (n + nb - 1) / nb;
+    size_t *cnt = (size_t *)calloc(nb + 1, sizeof(size_t));
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (size_t b = 0; b < nb; b++) { size_t c = 0; for (size_t i = b * per; i < n && i < (b + 1) * per; i++) c += keep[i] != 0; cnt[b + 1] = c; }
+    for (size_t b = 0; b < nb; b++) cnt[b + 1] += cnt[b];
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (size_t b = 0; b < nb; b++) { size_t o = cnt[b]; for (size_t i = b * per; i < n && i < (b + 1) * per; i++) if (keep[i]) { memcpy(dst + 4 * o, src + 4 * i, 32); o++; } }
+    const size_t total = cnt[nb];
+    free(cnt);
+    return total;
+}
+
+int orc_groth16_prove_program(const orc_pk *pk, const orc_program *prog, const uint8_t *infinity_a, const uint8_t *infinity_b,
+                              uint64_t commitment_index, const uint64_t *inputs_mont, const uint64_t *r_plain, const uint64_t *s_plain,
+                              uint8_t *out, double *seconds, uint64_t *err_at, int threads) {
+    if (threads <= 0) threads = omp_get_max_threads();
+    const size_t nw = prog->n_wires, m = prog->n_constraints;
+    uint64_t *w = (uint64_t *)malloc(32 * nw), *a = (uint64_t *)malloc(32 * m), *b = (uint64_t *)malloc(32 * m), *c = (uint64_t *)malloc(32 * m);
+    commit_ctx cc; memset(&cc, 0, sizeof(cc)); cc.pk = pk; cc.threads = threads;
+    double t0 = omp_get_wtime();
+    int rc = orc_solve(prog, inputs_mont, w, a, b, c, commit_cb, &cc, err_at, threads);
+    double t1 = omp_get_wtime();
+    if (rc == 0) {
+        uint8_t *keep = (uint8_t *)malloc(nw);
+        uint64_t *wa = (uint64_t *)malloc(32 * nw), *wb = (uint64_t *)malloc(32 * nw), *wk = (uint64_t *)malloc(32 * nw);
+        for (size_t i = 0; i < nw; i++) keep[i] = !infinity_a[i];
+        const size_t na = compact32(w, nw, keep, wa, threads);
+        for (size_t i = 0; i < nw; i++) keep[i] = !infinity_b[i];
+        const size_t nb = compact32(w, nw, keep, wb, threads);
+        for (size_t i = 0; i < nw; i++) keep[i] = i >= prog->n_public;
+        for (size_t i = 0; i < prog->n_committed; i++) keep[prog->private_committed[i]] = 0;
+        if (cc.committed) keep[commitment_index] = 0;
+        const size_t nk = compact32(w, nw, keep, wk, threads);
+        if (na != pk->n_a || nb != pk->n_b || nk != pk->n_k) rc = -2;
+        else rc = prove_core(pk, wa, wb, wk, cc.committed, a, b, c, m, r_plain, s_plain, out, threads, cc.committed ? &cc.commit : NULL);
+        free(keep); free(wa); free(wb); free(wk);
+    }
+    if (seconds) { seconds[0] = t1 - t0; seconds[1] = omp_get_wtime() - t1; }
+    free(cc.committed); free(w); free(a); free(b); free(c);
+    return rc;
 }

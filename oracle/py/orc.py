@@ -266,3 +266,99 @@ def poly_eval_bitrev(coef_mont: np.ndarray, logn: int, x0: int, threads=0) -> in
     x = fr_mont([x0]); out = np.zeros(4, dtype=np.uint64)
     lib().orc_poly_eval_bitrev(_p(a), C.c_int(logn), _p(x), _p(out), C.c_int(threads))
     return fr_unmont(out)[0]
+
+
+# ----------------------------------------------------------------------------- r1cs.Solve over the flat program (orc_solver.c)
+class OrcProgram(C.Structure):
+    _fields_ = ([("n_wires", C.c_uint64), ("n_public", C.c_uint64), ("n_secret", C.c_uint64), ("n_constraints", C.c_uint64)] +
+                [(f"{m}_{k}", C.c_void_p) for m in "lro" for k in ("row_ptr", "wire", "coeff")] +
+                [("coeffs", C.c_void_p), ("n_coeffs", C.c_uint64), ("n_instr", C.c_uint64), ("instr_kind", C.c_void_p), ("instr_arg", C.c_void_p),
+                 ("n_levels", C.c_uint64), ("level_ptr", C.c_void_p), ("level_instr", C.c_void_p), ("n_hints", C.c_uint64),
+                 ("hint_fn", C.c_void_p), ("hint_param", C.c_void_p), ("hint_out_first", C.c_void_p), ("hint_n_out", C.c_void_p),
+                 ("hint_in_ptr", C.c_void_p), ("hint_in_end", C.c_void_p), ("aux_row_ptr", C.c_void_p), ("aux_wire", C.c_void_p),
+                 ("aux_coeff", C.c_void_p), ("table_ptr", C.c_void_p), ("private_committed", C.c_void_p), ("n_committed", C.c_uint64)])
+
+
+COMMIT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p)
+SOLVE_ERRORS = {1: "more than one unsolved wire", 2: "division by zero", 3: "index outside a table", 4: "unknown hint", 5: "hint reads an unsolved wire",
+                6: "commitment hint without callback", 7: "committed wire unsolved", 8: "wire never solved", 9: "constraint not satisfied"}
+
+
+def program_struct(flat: dict):
+    """(OrcProgram, keep-alive list) from circuit_synth.flatten() output (numpy arrays)"""
+    keep = []
+
+    def arr(x, dt):
+        a = np.ascontiguousarray(np.asarray(x), dtype=dt)
+        if a.size == 0:
+            a = np.zeros(1, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    p = OrcProgram()
+    p.n_wires, p.n_public, p.n_secret, p.n_constraints = flat["n_wires"], flat["n_public"], flat["n_secret"], flat["n_constraints"]
+    for m in "lro":
+        setattr(p, f"{m}_row_ptr", arr(flat[f"{m}_row_ptr"], np.uint64))
+        setattr(p, f"{m}_wire", arr(flat[f"{m}_wire"], np.uint32)); setattr(p, f"{m}_coeff", arr(flat[f"{m}_coeff"], np.uint32))
+    tab = fr_mont(flat["coeffs"]); keep.append(tab)
+    p.coeffs, p.n_coeffs = tab.ctypes.data, len(flat["coeffs"])
+    p.n_instr, p.instr_kind, p.instr_arg = flat["n_instr"], arr(flat["instr_kind"], np.uint8), arr(flat["instr_arg"], np.uint32)
+    p.n_levels, p.level_ptr, p.level_instr = flat["n_levels"], arr(flat["level_ptr"], np.uint64), arr(flat["level_instr"], np.uint32)
+    p.n_hints = flat["n_hints"]
+    for k in ("hint_fn", "hint_param", "hint_out_first", "hint_n_out"):
+        setattr(p, k, arr(flat[k], np.uint32))
+    p.hint_in_ptr, p.hint_in_end = arr(flat["hint_in_ptr"], np.uint64), arr(flat["hint_in_end"], np.uint64)
+    p.aux_row_ptr, p.aux_wire, p.aux_coeff = arr(flat["aux_row_ptr"], np.uint64), arr(flat["aux_wire"], np.uint32), arr(flat["aux_coeff"], np.uint32)
+    p.table_ptr = arr(flat["table_ptr"], np.uint64)
+    p.private_committed, p.n_committed = arr(flat["private_committed"], np.uint64), len(flat["private_committed"])
+    return p, keep
+
+
+def solve(flat: dict, inputs_mont: np.ndarray, commit_fn=None, threads=0):
+    """r1cs.Solve on the CPU.  commit_fn(values_mont (n, 4) uint64) -> challenge as int.  Returns (wires, a, b, c) Montgomery arrays."""
+    p, keep = program_struct(flat)
+    w = np.zeros((flat["n_wires"], 4), dtype=np.uint64)
+    abc = [np.zeros((flat["n_constraints"], 4), dtype=np.uint64) for _ in range(3)]
+    ins = np.ascontiguousarray(inputs_mont, dtype=np.uint64)
+
+    def cb(vals, n, out, _user):
+        v = np.ctypeslib.as_array(C.cast(vals, C.POINTER(C.c_uint64)), shape=(max(n, 1), 4))[:n].copy()
+        ch = fr_mont([commit_fn(v) % bn.R])
+        C.memmove(out, ch.ctypes.data, 32)
+
+    err_at = C.c_uint64(0)
+    rc = lib().orc_solve(C.byref(p), _p(ins), _p(w), _p(abc[0]), _p(abc[1]), _p(abc[2]), COMMIT_FN(cb) if commit_fn else COMMIT_FN(), None,
+                         C.byref(err_at), C.c_int(threads))
+    if rc != 0:
+        raise RuntimeError(f"orc_solve: {SOLVE_ERRORS.get(rc, rc)} at {err_at.value}")
+    return w, abc[0], abc[1], abc[2]
+
+
+def commitment_challenge(raw64: bytes) -> int:
+    out = np.zeros(4, dtype=np.uint64)
+    buf = np.frombuffer(raw64, dtype=np.uint8).copy()
+    lib().orc_commitment_challenge(_p(buf), C.c_size_t(len(raw64)), _p(out))
+    return fr_unmont(out)[0]
+
+
+def groth16_prove_program(pkarr: dict, flat: dict, infinity_a, infinity_b, inputs_mont, r: int, s: int, threads=0):
+    """the whole groth16.Prove on the CPU: solver + proof.  Returns (proof bytes, (solve seconds, prove seconds))."""
+    keep = {k: np.ascontiguousarray(v, dtype=np.uint64) for k, v in pkarr.items() if k != "log_n"}
+    pk = OrcPk()
+    pk.n_a, pk.n_b, pk.n_k, pk.n_z, pk.n_ck = (keep["A"].size // 8, keep["B1"].size // 8, keep["K"].size // 8,
+                                                keep["Z"].size // 8, keep["ck_basis"].size // 8)
+    for k in ("A", "B1", "K", "Z", "B2", "ck_basis", "ck_basis_exp_sigma", "alpha1", "beta1", "delta1", "beta2", "delta2"):
+        setattr(pk, k, keep[k].ctypes.data)
+    pk.log_n = pkarr["log_n"]
+    p, keep2 = program_struct(flat)
+    ia = np.ascontiguousarray(infinity_a, dtype=np.uint8); ib = np.ascontiguousarray(infinity_b, dtype=np.uint8)
+    ins = np.ascontiguousarray(inputs_mont, dtype=np.uint64)
+    rs = ints_to_limbs([r % bn.R, s % bn.R])
+    out = np.empty(388, dtype=np.uint8)
+    secs = (C.c_double * 2)()
+    err_at = C.c_uint64(0)
+    rc = lib().orc_groth16_prove_program(C.byref(pk), C.byref(p), _p(ia), _p(ib), C.c_uint64(max(0, int(flat["commitment_index"]))), _p(ins),
+                                         _p(rs[0]), _p(rs[1]), _p(out), secs, C.byref(err_at), C.c_int(threads))
+    if rc != 0:
+        raise RuntimeError(f"orc_groth16_prove_program: {SOLVE_ERRORS.get(rc, rc)} at {err_at.value}")
+    return out.tobytes(), (secs[0], secs[1])

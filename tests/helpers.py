@@ -128,3 +128,33 @@ def r1cs_csr(cs):
             rp.append(len(wi))
         mats.append((np.array(rp, dtype=np.uint64), np.array(wi, dtype=np.uint32), np.array(ci, dtype=np.uint32)))
     return mats, orc.fr_mont(table)
+
+
+# ----------------------------------------------------------------------------------------------- circuit-shaped instances (solver tests)
+def oracle_poseidon_constants(t):
+    import poseidon as ps
+    rc, mds = ps.constants(t)
+    return rc, mds, ps.ROUNDS_P[t - 2]
+
+
+def circuit_synth():
+    import importlib
+    return importlib.import_module("zkmerkle-proof-of-solvency_b200.circuit_synth")
+
+
+def circuit_instance(seed=1, with_key=True, **shape):
+    """A BatchCreateUser-shaped circuit (circuit_synth.batch_create_user_like), its flat program, a satisfying input assignment
+    and -- with_key -- a Groth16 key made by the oracle's Setup from explicit toxic waste."""
+    cs_mod = circuit_synth()
+    cb = cs_mod.batch_create_user_like(poseidon_constants=oracle_poseidon_constants, **shape)
+    flat = cb.flatten()
+    inputs = cs_mod.draw_inputs(flat, seed)                       # canonical limbs
+    ints = [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in inputs]
+    inst = dict(flat=flat, inputs=ints, inputs_mont=orc.fr_mont(ints))
+    if with_key:
+        import solver
+        cs = solver.to_r1cs(flat)
+        tox = g16.toxic_from_seed(seed + 1)
+        sc = g16.setup_scalars(cs, tox)
+        inst.update(cs=cs, tox=tox, sc=sc, arr=pk_arrays(sc, tox))
+    return inst

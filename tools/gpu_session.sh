@@ -1,8 +1,22 @@
 #!/bin/bash
-# Development helper: what one `gpurun -- bash tools/gpu_session.sh` call runs.  EVERY step has its own short timeout: a kernel
-# that hangs must cost a minute, not the round's GPU budget (it did once: profiles/r01_SUMMARY.md, "two lanes per G2 bucket").
+# Development helper: what one `gpurun -- bash tools/gpu_session.sh [steps...]` call runs.  EVERY step has its own short timeout: a
+# kernel that hangs must cost a minute, not the round's GPU budget (it did once: profiles/r01_SUMMARY.md, "two lanes per G2 bucket").
+# steps: solver tests bench22 bench26 ref26 ncu_launches ncu_poseidon microbench
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 180 python -m pytest tests -m gpu -x -q > gpurun_out/s_tests.log 2>&1; rc=$?; echo "tests rc=$rc"; tail -4 gpurun_out/s_tests.log
-[ $rc -ne 0 ] && exit $rc        # nothing else is queued behind a failing or hanging test run
-timeout 240 python bench.py --no-cpu > gpurun_out/s_bench.json 2> gpurun_out/s_bench.err; echo "bench rc=$?"; tail -c 400 gpurun_out/s_bench.json
+steps="${@:-solver tests bench22}"
+for st in $steps; do
+  case $st in
+    solver)  timeout 600 python -m pytest tests/test_gpu_solver.py -x -q > gpurun_out/s_solver.log 2>&1; rc=$?; echo "solver tests rc=$rc"; tail -15 gpurun_out/s_solver.log
+             [ $rc -ne 0 ] && exit $rc ;;
+    tests)   timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_solver.py > gpurun_out/s_tests.log 2>&1; rc=$?; echo "tests rc=$rc"; tail -6 gpurun_out/s_tests.log
+             [ $rc -ne 0 ] && exit $rc ;;
+    bench22) timeout 600 python bench.py --log-n 22 --cpu-log-n 18 > gpurun_out/s_bench22.json 2> gpurun_out/s_bench22.err; echo "bench22 rc=$?"; tail -c 1500 gpurun_out/s_bench22.json; tail -5 gpurun_out/s_bench22.err ;;
+    bench26) timeout 1200 python bench.py --no-cpu > gpurun_out/s_bench26.json 2> gpurun_out/s_bench26.err; echo "bench26 rc=$?"; tail -c 2500 gpurun_out/s_bench26.json; tail -5 gpurun_out/s_bench26.err ;;
+    bench26cpu) timeout 1500 python bench.py > gpurun_out/s_bench26.json 2> gpurun_out/s_bench26.err; echo "bench26 rc=$?"; tail -c 2500 gpurun_out/s_bench26.json; tail -5 gpurun_out/s_bench26.err ;;
+    ref26)   timeout 1700 python bench.py --impl reference > gpurun_out/s_ref26.json 2> gpurun_out/s_ref26.err; echo "ref26 rc=$?"; tail -c 1500 gpurun_out/s_ref26.json; tail -5 gpurun_out/s_ref26.err ;;
+    ref24)   timeout 900 python bench.py --impl reference --log-n 24 > gpurun_out/s_ref24.json 2> gpurun_out/s_ref24.err; echo "ref24 rc=$?"; tail -c 1500 gpurun_out/s_ref24.json; tail -5 gpurun_out/s_ref24.err ;;
+    ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_bench22.csv python bench.py --log-n 22 --steps 1 --warmup 1 --no-cpu --no-e2e --no-parity > gpurun_out/s_ncu_l.log 2>&1; echo "ncu launches rc=$?" ;;
+    *) echo "unknown step $st" ;;
+  esac
+done

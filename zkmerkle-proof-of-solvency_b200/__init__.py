@@ -116,6 +116,19 @@ def padding_account_assets(assets) -> np.ndarray:
     return flat
 
 
+def poseidon_constants(t: int):
+    """(round constants, MDS rows, partial rounds) of the width-t permutation as canonical ints, from the library's own generator"""
+    rc = np.zeros(((8 + 70) * t, 4), dtype=np.uint64)
+    mds = np.zeros((t * t, 4), dtype=np.uint64)
+    rp = C.c_uint32(0)
+    _check(lib().zkpor_poseidon_constants(C.c_uint32(t), _ptr(rc), _ptr(mds), C.byref(rp)))
+    r_inv = pow(1 << 256, -1, R_MOD)
+    unmont = lambda row: (int(row[0]) | int(row[1]) << 64 | int(row[2]) << 128 | int(row[3]) << 192) * r_inv % R_MOD
+    rcs = [unmont(rc[i]) for i in range((8 + rp.value) * t)]
+    m = [unmont(x) for x in mds]
+    return rcs, [m[i * t:(i + 1) * t] for i in range(t)], rp.value
+
+
 def be32(v: int) -> bytes:
     return int(v).to_bytes(32, "big")
 
@@ -460,6 +473,15 @@ class ProvingKey:
                                          _ptr(out), C.byref(n)))
         return out[:n.value].tobytes()
 
+    def prove_solve(self, prog: "Program", inputs, r: int, s: int) -> bytes:
+        """the whole of groth16.Prove (prover.go:269): witness solver (hints, commitment mid-solve) + proof, from the circuit inputs"""
+        out = np.zeros(388, dtype=np.uint8)
+        n = C.c_uint32(0)
+        rb = (C.c_uint8 * 32).from_buffer_copy(be32(r % R_MOD))
+        sb = (C.c_uint8 * 32).from_buffer_copy(be32(s % R_MOD))
+        _check(lib().zkpor_groth16_prove_solve(self.ctx._h, self._h, prog._h, _ptr(inputs), rb, sb, _ptr(out), C.byref(n)))
+        return out[:n.value].tobytes()
+
     def prove_wires(self, cs: "R1CS", wires, r: int, s: int) -> bytes:
         """groth16.Prove from the wire vector alone: a, b, c = L w, R w, O w are evaluated on the device (R1CS resident in HBM)."""
         out = np.zeros(388, dtype=np.uint8)
@@ -605,6 +627,94 @@ class R1CS:
         outs = [np.zeros((self.n_constraints, 4), dtype=np.uint64) for _ in range(3)]
         _check(lib().zkpor_r1cs_eval(self.ctx._h, self._h, _ptr(wires), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2])))
         return outs
+
+
+# ----------------------------------------------------------------------------------------------- witness solver
+class ProgramDesc(C.Structure):
+    _fields_ = [("n_wires", C.c_uint64), ("n_public", C.c_uint64), ("n_secret", C.c_uint64), ("n_constraints", C.c_uint64),
+                ("l", Csr), ("r", Csr), ("o", Csr), ("coeff_table", C.c_void_p), ("n_coeffs", C.c_uint64),
+                ("n_instr", C.c_uint64), ("instr_kind", C.c_void_p), ("instr_arg", C.c_void_p),
+                ("n_levels", C.c_uint64), ("level_ptr", C.c_void_p), ("level_instr", C.c_void_p),
+                ("n_hints", C.c_uint64), ("hint_fn", C.c_void_p), ("hint_param", C.c_void_p), ("hint_out_first", C.c_void_p),
+                ("hint_n_out", C.c_void_p), ("hint_in_ptr", C.c_void_p), ("hint_in_end", C.c_void_p),
+                ("n_aux_rows", C.c_uint64), ("aux", Csr), ("n_tables", C.c_uint64), ("table_ptr", C.c_void_p)]
+
+
+def fr_mont_limbs(values) -> np.ndarray:
+    """canonical ints -> (k, 4) uint64 Montgomery limbs (fr.Element memory layout); host-side, for coefficient tables"""
+    out = np.zeros((len(values), 4), dtype=np.uint64)
+    for i, v in enumerate(values):
+        m = (int(v) % R_MOD) * (1 << 256) % R_MOD
+        out[i] = [(m >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)]
+    return out
+
+
+class Program:
+    """gnark's compiled constraint system, flattened (zkpor_program_desc), resident in HBM: matrices, instructions, levels, hints.
+    `flat` = the dict circuit_synth.CircuitBuilder.flatten() returns (numpy arrays, or torch tensors already on the device)."""
+
+    def __init__(self, ctx: Context, flat: dict):
+        self.ctx = ctx
+        self.n_wires, self.n_constraints = int(flat["n_wires"]), int(flat["n_constraints"])
+        self.n_inputs = int(flat["n_public"]) - 1 + int(flat["n_secret"])
+        keep = []
+
+        def hp(x, dtype):
+            if isinstance(x, np.ndarray):
+                x = np.ascontiguousarray(x, dtype=dtype)
+            keep.append(x)
+            return _ptr(x) if len(x) else None
+
+        def csr(prefix):
+            return Csr(len(flat[prefix + "_wire"]), hp(flat[prefix + "_row_ptr"], np.uint64), hp(flat[prefix + "_wire"], np.uint32), hp(flat[prefix + "_coeff"], np.uint32))
+
+        d = ProgramDesc()
+        d.n_wires, d.n_public, d.n_secret, d.n_constraints = self.n_wires, int(flat["n_public"]), int(flat["n_secret"]), self.n_constraints
+        d.l, d.r, d.o = csr("l"), csr("r"), csr("o")
+        tab = fr_mont_limbs(flat["coeffs"])
+        keep.append(tab)
+        d.coeff_table, d.n_coeffs = _ptr(tab), tab.shape[0]
+        d.n_instr, d.instr_kind, d.instr_arg = int(flat["n_instr"]), hp(flat["instr_kind"], np.uint8), hp(flat["instr_arg"], np.uint32)
+        d.n_levels, d.level_ptr, d.level_instr = int(flat["n_levels"]), hp(flat["level_ptr"], np.uint64), hp(flat["level_instr"], np.uint32)
+        d.n_hints = int(flat["n_hints"])
+        d.hint_fn, d.hint_param = hp(flat["hint_fn"], np.uint32), hp(flat["hint_param"], np.uint32)
+        d.hint_out_first, d.hint_n_out = hp(flat["hint_out_first"], np.uint32), hp(flat["hint_n_out"], np.uint32)
+        d.hint_in_ptr, d.hint_in_end = hp(flat["hint_in_ptr"], np.uint64), hp(flat["hint_in_end"], np.uint64)
+        d.n_aux_rows = len(flat["aux_row_ptr"]) - 1
+        d.aux = csr("aux")
+        d.n_tables, d.table_ptr = int(flat["n_tables"]), hp(np.asarray(flat["table_ptr"], dtype=np.uint64), np.uint64)
+        self._h = C.c_void_p()
+        _check(lib().zkpor_program_upload(ctx._h, C.byref(d), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().zkpor_program_free(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        _check(lib().zkpor_program_stats(self._h, out))
+        return dict(wide_levels=out[0], narrow_runs=out[1], narrow_levels=out[2], count_hints=out[3])
+
+    def solve(self, inputs, pk: "ProvingKey" = None, want_abc=True):
+        """r1cs.Solve: inputs = (n_public - 1 + n_secret, 4) uint64 Montgomery -> (wires, a, b, c, commitment) as numpy arrays"""
+        w = np.zeros((self.n_wires, 4), dtype=np.uint64)
+        abc = [np.zeros((self.n_constraints, 4), dtype=np.uint64) for _ in range(3)] if want_abc else [None] * 3
+        cm = np.zeros(8, dtype=np.uint64)
+        _check(lib().zkpor_r1cs_solve(self.ctx._h, self._h, pk._h if pk is not None else None, _ptr(inputs), _ptr(w), _ptr(abc[0]), _ptr(abc[1]),
+                                      _ptr(abc[2]), _ptr(cm)))
+        return w, abc[0], abc[1], abc[2], cm
+
+    def solve_device(self, inputs, d_wires, pk: "ProvingKey" = None, abc=(None, None, None)):
+        """solve with inputs / wires (and optionally a, b, c) resident in HBM: tensors or raw device pointers"""
+        _check(lib().zkpor_r1cs_solve(self.ctx._h, self._h, pk._h if pk is not None else None, _ptr(inputs), _ptr(d_wires), _ptr(abc[0]), _ptr(abc[1]),
+                                      _ptr(abc[2]), None))
 
 
 # ----------------------------------------------------------------------------------------------- pairing / Verify

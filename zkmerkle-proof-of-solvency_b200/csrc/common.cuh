@@ -35,7 +35,7 @@ const char *get_error();
     } while (0)
 
 // stages whose device time is recorded per call (zkpor_ctx_last_timings)
-enum Stage { ST_H2D = 0, ST_DIGITS, ST_SORT, ST_ACCUM, ST_REDUCE, ST_NTT, ST_POSEIDON, ST_D2H, ST_COUNT };
+enum Stage { ST_H2D = 0, ST_DIGITS, ST_SORT, ST_ACCUM, ST_REDUCE, ST_NTT, ST_POSEIDON, ST_D2H, ST_SOLVE, ST_COUNT };
 
 // kernel classes whose individual launches are timed with CUDA events (zkpor_ctx_kernel_stats; bench.py's roofline)
 enum KClass { KC_ACCUM_G1 = 0, KC_ACCUM_G2, KC_NTT_PASS, KC_SORT, KC_POSEIDON, KC_COUNT };

@@ -32,7 +32,7 @@ void g2_to_raw_bytes(uint8_t out[128], const ec::G2Affine &p) {
     fp_to_be32(out, p.x.a1); fp_to_be32(out + 32, p.x.a0); fp_to_be32(out + 64, p.y.a1); fp_to_be32(out + 96, p.y.a0);
 }
 
-static const char *STAGE_NAMES[ST_COUNT] = {"h2d", "digits", "sort", "accumulate", "reduce", "ntt", "poseidon", "d2h"};
+static const char *STAGE_NAMES[ST_COUNT] = {"h2d", "digits", "sort", "accumulate", "reduce", "ntt", "poseidon", "d2h", "solve"};
 
 }  // namespace zk
 

@@ -17,18 +17,6 @@
 using namespace ff;
 using namespace ec;
 
-struct zkpor_pk {
-    uint32_t log_n = 0;
-    uint64_t n_wires = 0, n_a = 0, n_b = 0, n_k = 0, n_z = 0, n_ck = 0;
-    G1Affine *A = nullptr, *B1 = nullptr, *K = nullptr, *Z = nullptr, *ck = nullptr, *ck_sigma = nullptr;
-    G2Affine *B2 = nullptr;
-    uint32_t *idx_c = nullptr;                                     // gather indices of the committed wires
-    uint2 *map_a = nullptr, *map_b = nullptr, *map_k = nullptr;   // wire -> key-point maps of the shared sort (msm.cu map_wire)
-    G1Affine alpha1, beta1, delta1;
-    G2Affine beta2, delta2;
-    bool has_commitment = false;
-    zk::DevBuf wires, sub;
-};
 
 namespace zk {
 
@@ -64,6 +52,8 @@ static void assemble_proof(const ProofParts &pp, const G1Affine &alpha1, const G
                            uint32_t *out_len) {
     Fr r_plain, s_plain;
     fe_from_be32(&r_plain, r_be); fe_from_be32(&s_plain, s_be);
+    // gnark draws r, s with fr.Element.SetRandom: canonical by construction; bytes >= the modulus are reduced (fr.SetBytes semantics)
+    r_plain = Fr::from_mont(Fr::to_mont(r_plain)); s_plain = Fr::from_mont(Fr::to_mont(s_plain));
     Fr kr = Fr::from_mont(Fr::neg(Fr::mul(Fr::to_mont(r_plain), Fr::to_mont(s_plain))));   // -(r*s), plain
     G1XYZZ d1 = G1XYZZ::from_affine(delta1);
     G1XYZZ ar = pp.ar; ar.add_affine(alpha1, false); ar.add(d1.mul_256(r_plain.l));
@@ -84,6 +74,19 @@ static void assemble_proof(const ProofParts &pp, const G1Affine &alpha1, const G
         g1_to_raw_bytes(out + len, G1Affine::inf()); len += 64;
     }
     *out_len = len;
+}
+
+int32_t pk_commit_and_pok(zkpor_ctx *ctx, zkpor_pk *pk, const Fr *d_wires, G1XYZZ *commit, G1XYZZ *pok) {
+    *commit = G1XYZZ::inf(); *pok = G1XYZZ::inf();
+    if (!pk->has_commitment || pk->n_ck == 0) return ZKPOR_OK;
+    ZK_TRY(pk->sub.reserve(pk->n_ck * 32));
+    Fr *sub = pk->sub.as<Fr>();
+    MsmSorted srt;
+    ZK_LAUNCH(ctx, k_gather_fr, grid_for(pk->n_ck, 256), 256, 0, d_wires, (const uint32_t *)pk->idx_c, pk->n_ck, sub);
+    ZK_TRY(msm_sort(ctx, sub, pk->n_ck, ZKPOR_SCALARS_MONT, &srt));
+    ZK_TRY(msm_accumulate_g1(ctx, pk->ck, srt, commit));
+    ZK_TRY(msm_accumulate_g1(ctx, pk->ck_sigma, srt, pok));
+    return ZKPOR_OK;
 }
 
 }  // namespace zk
@@ -107,6 +110,8 @@ int32_t zkpor_pk_upload(zkpor_ctx *ctx, const zkpor_pk_desc *d, zkpor_pk **out) 
     ZK_REQUIRE(d->log_n >= 1 && d->log_n <= 28, "pk_upload: log_n out of range");
     ZK_REQUIRE(d->g1_alpha && d->g1_beta && d->g1_delta && d->g2_beta && d->g2_delta, "pk_upload: missing alpha/beta/delta");
     ZK_REQUIRE(d->n_wires < (1ull << 32), "pk_upload: too many wires");
+    ZK_REQUIRE(d->n_committed == 0 || (d->ck_basis && d->ck_basis_exp_sigma && (d->n_wires == 0 || d->private_committed)),
+               "pk_upload: n_committed > 0 needs ck_basis, ck_basis_exp_sigma and (with wire maps) private_committed");
     ZK_CUDA(cudaSetDevice(ctx->device));
     zkpor_pk *pk = new zkpor_pk();
     *out = nullptr;
@@ -181,8 +186,9 @@ int32_t zkpor_pk_commit(zkpor_ctx *ctx, zkpor_pk *pk, const void *committed_valu
 }
 
 // shared body of zkpor_groth16_prove (a, b, c from the caller) and zkpor_groth16_prove_wires (a, b, c = L w, R w, O w on the device)
-static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, const void *wires, const void *a, const void *b, const void *c,
-                          uint64_t n_constraints, const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
+// and zkpor_groth16_prove_solve (the wires themselves come from the device solver: `prog` set, `wires` = the circuit's inputs)
+static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_program *prog, const void *wires, const void *a, const void *b,
+                          const void *c, uint64_t n_constraints, const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
     ZK_REQUIRE(pk->n_wires > 0, "prove: key was uploaded without wire maps (sharded key?)");
     const size_t n = (size_t)1 << pk->log_n;
     ZK_REQUIRE(n_constraints > 0 && n_constraints <= n, "prove: n_constraints exceeds the domain");
@@ -191,9 +197,27 @@ static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, const vo
     // wires -> HBM on the compute stream (every wire-only MSM needs them); a, b, c -> padded device vectors on the
     // copy stream, so that their H2D transfer overlaps the commitment / A / B / K multi-scalar multiplications
     const void *dw;
-    stage_begin(ctx, ST_H2D);
-    ZK_TRY(to_device(ctx, wires, pk->n_wires * 32, pk->wires, &dw));
-    stage_end(ctx, ST_H2D);
+    ProofParts pp;
+    pp.commit = G1XYZZ::inf(); pp.pok = G1XYZZ::inf();
+    bool commit_done = false;
+    if (prog != nullptr) {
+        // r1cs.Solve on the device: inputs -> wires[1 ..], every other wire by the level schedule; the commitment hint leaves the
+        // commitment and its proof of knowledge behind
+        ZK_TRY(pk->wires.reserve(pk->n_wires * 32));
+        Fr *w = pk->wires.as<Fr>();
+        const Fr one = Fr::one();
+        stage_begin(ctx, ST_H2D);
+        ZK_CUDA(cudaMemcpyAsync(w, &one, 32, cudaMemcpyHostToDevice, ctx->stream));
+        ZK_CUDA(cudaMemcpyAsync(w + 1, wires, program_inputs(prog) * 32, cudaMemcpyDefault, ctx->stream));
+        stage_end(ctx, ST_H2D);
+        stage_begin(ctx, ST_SOLVE);
+        ZK_TRY(solver_run(ctx, prog, pk, w, &pp.commit, &pp.pok, &commit_done));
+        dw = w;
+    } else {
+        stage_begin(ctx, ST_H2D);
+        ZK_TRY(to_device(ctx, wires, pk->n_wires * 32, pk->wires, &dw));
+        stage_end(ctx, ST_H2D);
+    }
     const size_t bytes = n * sizeof(Fr), in_bytes = n_constraints * sizeof(Fr);
     ZK_TRY(ctx->ntt_a.reserve(bytes)); ZK_TRY(ctx->ntt_b.reserve(bytes)); ZK_TRY(ctx->ntt_c.reserve(bytes));
     const void *src[3] = {a, b, c};
@@ -203,6 +227,10 @@ static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, const vo
         // constraint evaluation on the device: needs only the wires, runs ahead of the multiplications on the compute stream
         for (int k = 0; k < 3; k++) if (bytes > in_bytes) ZK_CUDA(cudaMemsetAsync((uint8_t *)dst[k] + in_bytes, 0, bytes - in_bytes, ctx->stream));
         ZK_TRY(r1cs_eval_dev(ctx, cs, (const Fr *)dw, dst[0], dst[1], dst[2]));
+        if (prog != nullptr) {   // gnark's Solve fails on the first unsatisfied constraint; here one pass over a, b, c
+            ZK_TRY(r1cs_check_dev(ctx, dst[0], dst[1], dst[2], n_constraints));
+            stage_end(ctx, ST_SOLVE);
+        }
     } else {
         for (int k = 0; k < 3; k++) {
             ZK_CUDA(cudaMemcpyAsync(dst[k], src[k], in_bytes, cudaMemcpyDefault, ctx->copy_stream));
@@ -225,17 +253,8 @@ static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, const vo
     }
     ZK_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
 
-    ZK_TRY(pk->sub.reserve((pk->n_ck ? pk->n_ck : 1) * 32));
-    Fr *sub = pk->sub.as<Fr>();
-    ProofParts pp;
-    pp.commit = G1XYZZ::inf(); pp.pok = G1XYZZ::inf();
     MsmSorted srt;
-    if (pk->has_commitment && pk->n_ck) {
-        ZK_LAUNCH(ctx, k_gather_fr, grid_for(pk->n_ck, 256), 256, 0, (const Fr *)dw, (const uint32_t *)pk->idx_c, pk->n_ck, sub);
-        ZK_TRY(msm_sort(ctx, sub, pk->n_ck, ZKPOR_SCALARS_MONT, &srt));
-        ZK_TRY(msm_accumulate_g1(ctx, pk->ck, srt, &pp.commit));
-        ZK_TRY(msm_accumulate_g1(ctx, pk->ck_sigma, srt, &pp.pok));
-    }
+    if (!commit_done) ZK_TRY(pk_commit_and_pok(ctx, pk, (const Fr *)dw, &pp.commit, &pp.pok));
     pp.ar = G1XYZZ::inf(); pp.bs1 = G1XYZZ::inf(); pp.bs2 = G2XYZZ::inf(); pp.krs_k = G1XYZZ::inf(); pp.krs_z = G1XYZZ::inf();
     // one digit extraction + counting sort over the whole wire vector, four accumulations through their wire maps
     ZK_TRY(msm_sort(ctx, dw, pk->n_wires, ZKPOR_SCALARS_MONT, &srt));
@@ -264,14 +283,22 @@ static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, const vo
 int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, const void *a, const void *b, const void *c,
                             uint64_t n_constraints, const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
     ZK_REQUIRE(ctx && pk && wires && a && b && c && r_be && s_be && out_proof && out_len, "prove: null argument");
-    return prove_impl(ctx, pk, nullptr, wires, a, b, c, n_constraints, r_be, s_be, out_proof, out_len);
+    return prove_impl(ctx, pk, nullptr, nullptr, wires, a, b, c, n_constraints, r_be, s_be, out_proof, out_len);
 }
 
 int32_t zkpor_groth16_prove_wires(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, const void *wires, const uint8_t r_be[32], const uint8_t s_be[32],
                                   uint8_t *out_proof, uint32_t *out_len) {
     ZK_REQUIRE(ctx && pk && cs && wires && r_be && s_be && out_proof && out_len, "prove_wires: null argument");
     ZK_REQUIRE(r1cs_wires(cs) == pk->n_wires, "prove_wires: the constraint system and the key disagree on the number of wires");
-    return prove_impl(ctx, pk, cs, wires, nullptr, nullptr, nullptr, r1cs_rows(cs), r_be, s_be, out_proof, out_len);
+    return prove_impl(ctx, pk, cs, nullptr, wires, nullptr, nullptr, nullptr, r1cs_rows(cs), r_be, s_be, out_proof, out_len);
+}
+
+int32_t zkpor_groth16_prove_solve(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_program *prog, const void *inputs, const uint8_t r_be[32],
+                                  const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
+    ZK_REQUIRE(ctx && pk && prog && inputs && r_be && s_be && out_proof && out_len, "prove_solve: null argument");
+    zkpor_r1cs *cs = program_matrices(prog);
+    ZK_REQUIRE(r1cs_wires(cs) == pk->n_wires, "prove_solve: the program and the key disagree on the number of wires");
+    return prove_impl(ctx, pk, cs, prog, inputs, nullptr, nullptr, nullptr, r1cs_rows(cs), r_be, s_be, out_proof, out_len);
 }
 
 int32_t zkpor_groth16_prove_partial(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires_a, const void *wires_b, const void *wires_k,

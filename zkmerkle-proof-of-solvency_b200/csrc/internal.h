@@ -3,6 +3,31 @@
 #include "common.cuh"
 #include "ec.cuh"
 
+// R1CS matrices resident in HBM (r1cs.cu)
+struct zkpor_r1cs {
+    uint64_t n_rows = 0, n_wires = 0, n_coeffs = 0;
+    uint64_t *row_ptr[3] = {nullptr, nullptr, nullptr};
+    uint32_t *wire_ids[3] = {nullptr, nullptr, nullptr}, *coeff_ids[3] = {nullptr, nullptr, nullptr};
+    uint64_t nnz[3] = {0, 0, 0};
+    ff::Fr *coeffs = nullptr;
+    uint32_t one_id = 0xFFFFFFFFu;   // id of the coefficient 1 (skips the product), if the table has it
+    zk::DevBuf wires, out;
+};
+
+// Groth16 proving key resident in HBM (groth16.cu)
+struct zkpor_pk {
+    uint32_t log_n = 0;
+    uint64_t n_wires = 0, n_a = 0, n_b = 0, n_k = 0, n_z = 0, n_ck = 0;
+    ec::G1Affine *A = nullptr, *B1 = nullptr, *K = nullptr, *Z = nullptr, *ck = nullptr, *ck_sigma = nullptr;
+    ec::G2Affine *B2 = nullptr;
+    uint32_t *idx_c = nullptr;                                     // gather indices of the committed wires
+    uint2 *map_a = nullptr, *map_b = nullptr, *map_k = nullptr;   // wire -> key-point maps of the shared sort (msm.cu map_wire)
+    ec::G1Affine alpha1, beta1, delta1;
+    ec::G2Affine beta2, delta2;
+    bool has_commitment = false;
+    zk::DevBuf wires, sub;
+};
+
 namespace zk {
 
 // Window plan of one Pippenger run: c-bit signed digits, nwin windows, nb = 2^(c-1) buckets per window.
@@ -49,6 +74,20 @@ int32_t msm_g2_dev(zkpor_ctx *ctx, const void *d_points, const void *d_scalars, 
 int32_t r1cs_eval_dev(zkpor_ctx *ctx, zkpor_r1cs *cs, const ff::Fr *d_wires, ff::Fr *d_a, ff::Fr *d_b, ff::Fr *d_c);
 uint64_t r1cs_rows(const zkpor_r1cs *cs);
 uint64_t r1cs_wires(const zkpor_r1cs *cs);
+
+// Pedersen commitment and proof of knowledge of the key's committed wires, gathered from the device wire vector (groth16.cu):
+// one sort, two accumulations.  Called mid-solve by the commitment hint and by the prove entry points that receive solved wires.
+int32_t pk_commit_and_pok(zkpor_ctx *ctx, zkpor_pk *pk, const ff::Fr *d_wires, ec::G1XYZZ *commit, ec::G1XYZZ *pok);
+// BSB22 challenge: hash_to_field("bsb22-commitment")(commitment.Marshal()) for a commitment without public committed wires (pairing.cu)
+ff::Fr commitment_challenge_g1(const ec::G1Affine &commitment);
+
+// witness solver (solver.cu): wires[0] = 1, wires[1 ..] = inputs on entry; every other wire is written.  commit / pok receive the
+// commitment hint's by-products when the program has one (has_commit).
+int32_t solver_run(zkpor_ctx *ctx, zkpor_program *prog, zkpor_pk *pk, ff::Fr *d_wires, ec::G1XYZZ *commit, ec::G1XYZZ *pok, bool *has_commit);
+zkpor_r1cs *program_matrices(zkpor_program *prog);
+uint64_t program_inputs(const zkpor_program *prog);
+// a[k]*b[k] == c[k] for every constraint row; ZKPOR_ERR_STATE naming the first violated row otherwise
+int32_t r1cs_check_dev(zkpor_ctx *ctx, const ff::Fr *d_a, const ff::Fr *d_b, const ff::Fr *d_c, uint64_t n_rows);
 
 // NTT (device-resident data)
 int32_t ntt_dev(zkpor_ctx *ctx, ff::Fr *d_data, uint32_t log_n, bool inverse, bool dit, bool coset);

@@ -27,6 +27,23 @@ __global__ void k_from_mont(const Fr *__restrict__ in, Fr *__restrict__ out, uin
     if (i < n) out[i] = Fr::from_mont(in[i]);
 }
 
+// plain scalars may be any 256-bit integers: bring them below r (at most five subtractions), so that the signed-digit recoding's
+// top carry always fits the windows sized for 254-bit values
+__global__ void k_canon_plain(const Fr *__restrict__ in, Fr *__restrict__ out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x = in[i];
+    const Fr m = Fr::modulus();
+    for (int k = 0; k < 6; k++) {
+        bool ge = true;
+        for (int j = 7; j >= 0; j--) { if (x.l[j] > m.l[j]) break; if (x.l[j] < m.l[j]) { ge = false; break; } }
+        if (!ge) break;
+        uint64_t borrow = 0;
+        for (int j = 0; j < 8; j++) { uint64_t t = (uint64_t)x.l[j] - m.l[j] - borrow; x.l[j] = (uint32_t)t; borrow = (t >> 63) & 1; }
+    }
+    out[i] = x;
+}
+
 __device__ __forceinline__ uint32_t window_bits(const uint32_t *s, uint32_t off, uint32_t c) {
     uint32_t limb = off >> 5, sh = off & 31;
     uint64_t v = s[limb];
@@ -356,11 +373,10 @@ int32_t msm_sort(zkpor_ctx *ctx, const void *d_scalars, uint64_t n, uint32_t fla
     ZK_TRY(ctx->sort_idx.reserve((size_t)plan.nwin * n * 4));
     stage_begin(ctx, ST_DIGITS);
     const uint32_t *plain = (const uint32_t *)d_scalars;
-    if (!(flags & ZKPOR_SCALARS_PLAIN)) {
-        ZK_TRY(ctx->misc.reserve(n * 32));
-        ZK_LAUNCH(ctx, k_from_mont, grid_for(n, 256), 256, 0, (const Fr *)d_scalars, ctx->misc.as<Fr>(), n);
-        plain = ctx->misc.as<uint32_t>();
-    }
+    ZK_TRY(ctx->misc.reserve(n * 32));
+    if (!(flags & ZKPOR_SCALARS_PLAIN)) ZK_LAUNCH(ctx, k_from_mont, grid_for(n, 256), 256, 0, (const Fr *)d_scalars, ctx->misc.as<Fr>(), n);
+    else ZK_LAUNCH(ctx, k_canon_plain, grid_for(n, 256), 256, 0, (const Fr *)d_scalars, ctx->misc.as<Fr>(), n);
+    plain = ctx->misc.as<uint32_t>();
     ZK_CUDA(cudaMemsetAsync(ctx->bucket_cnt.p, 0, slots * 4, ctx->stream));
     const bool partitioned = n >= (1u << 18) && plan.c >= PART_BITS + 2 && plan.nwin <= 32 && !ctx->direct_scatter;
     if (partitioned) {

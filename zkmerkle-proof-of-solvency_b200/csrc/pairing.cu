@@ -201,6 +201,12 @@ static Fr commitment_challenge(const G1Affine &commitment, const zkpor_vk_desc *
     return hash_to_fr(msg.data(), msg.size(), "bsb22-commitment");
 }
 
+Fr commitment_challenge_g1(const G1Affine &commitment) {
+    uint8_t msg[64];
+    g1_to_raw_bytes(msg, commitment);
+    return hash_to_fr(msg, 64, "bsb22-commitment");
+}
+
 static int32_t check_vk(const zkpor_vk_desc *vk, uint64_t n_public) {
     ZK_REQUIRE(vk && vk->g1_alpha && vk->g2_beta && vk->g2_gamma && vk->g2_delta && vk->g1_k, "verify: null verifying-key field");
     ZK_REQUIRE(vk->n_commitments <= 1, "verify: at most one BSB22 commitment is supported (the reference circuits have exactly one)");

@@ -536,6 +536,16 @@ int32_t zkpor_poseidon_set_out_lane(zkpor_ctx *ctx, int32_t lane) {
     return ZKPOR_OK;
 }
 
+int32_t zkpor_poseidon_constants(uint32_t t, void *out_round_constants, void *out_mds, uint32_t *out_rounds_p) {
+    ZK_REQUIRE(t >= 2 && t <= (uint32_t)MAX_T && out_round_constants && out_mds && out_rounds_p, "poseidon_constants: width must be 2..13, outputs non-null");
+    std::vector<Fr> rc, mds; int rp = 0;
+    build_constants((int)t, rc, mds, rp);
+    memcpy(out_round_constants, rc.data(), rc.size() * sizeof(Fr));
+    memcpy(out_mds, mds.data(), mds.size() * sizeof(Fr));
+    *out_rounds_p = (uint32_t)rp;
+    return ZKPOR_OK;
+}
+
 int32_t zkpor_poseidon_hash_batch(zkpor_ctx *ctx, const void *in_be, uint32_t n_in, uint64_t count, void *out_be) {
     ZK_REQUIRE(ctx != nullptr && in_be != nullptr && out_be != nullptr, "poseidon: null argument");
     ZK_REQUIRE(n_in >= 1, "poseidon: empty input");

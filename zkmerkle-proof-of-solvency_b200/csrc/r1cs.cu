@@ -7,15 +7,6 @@
 
 using namespace ff;
 
-struct zkpor_r1cs {
-    uint64_t n_rows = 0, n_wires = 0, n_coeffs = 0;
-    uint64_t *row_ptr[3] = {nullptr, nullptr, nullptr};
-    uint32_t *wire_ids[3] = {nullptr, nullptr, nullptr}, *coeff_ids[3] = {nullptr, nullptr, nullptr};
-    uint64_t nnz[3] = {0, 0, 0};
-    Fr *coeffs = nullptr;
-    uint32_t one_id = 0xFFFFFFFFu;   // id of the coefficient 1 (skips the product), if the table has it
-    zk::DevBuf wires, out;
-};
 
 namespace zk {
 

@@ -1,0 +1,563 @@
+// Witness solver on the GPU: gnark's r1cs.Solve (constraint/bn254/solver.go + system.go, out of tree) -- the first step of
+// groth16.Prove, src/prover/prover/prover.go:269 -- with the hint functions the reference circuit uses (IntegerDivision,
+// circuit/utils.go:103-110, registered at prover.go:68; gnark's std hints behind api.ToBinary / api.IsZero / rangecheck.Check /
+// logderivlookup; the BSB22 commitment placeholder that Prove overrides).
+//
+// gnark walks cs.Levels: the instructions of a level are independent, levels are barriers.  An R1C instruction has exactly one
+// unsolved wire, found at run time; here it is found ONCE, at upload, by a dry run of the same schedule on solved-flags, so the
+// solving kernels only evaluate and store.
+//
+// Schedule.  The reference circuit has two very different regimes: thousands of levels that are ~10^3..10^6
+// instructions wide (one block per user: range checks, lookups, Merkle paths) and a tail of ~10^5 levels that are 1..13 wide (the
+// two 10 000-element CEX commitments are serial sponge chains).  So:
+//   * a WIDE level is one grid launch, 8 lanes per instruction: the lanes split the terms of the three linear expressions
+//     (Poseidon rows carry up to ~80 terms), reduce with shuffles, lane 0 solves and stores;
+//   * a run of consecutive NARROW levels is ONE launch of a single CTA: a warp per instruction, __syncthreads between levels --
+//     a level then costs a dependent L2 round trip instead of a kernel launch;
+//   * COUNT (multiplicities) is a histogram over all queries; COMMIT gathers the committed wires, runs the Pedersen commitment and
+//     its proof of knowledge (one sort, two accumulations), hashes the point to the field on the host, stores the challenge.
+// The solver writes wire values only; a = Lw, b = Rw, c = Ow and the satisfaction check are one wide pass afterwards (r1cs.cu).
+#include "internal.h"
+#include <algorithm>
+
+using namespace ff;
+using namespace ec;
+
+namespace zk {
+
+static const uint32_t NARROW_MAX = 96;          // levels up to this many instructions are fused into single-CTA runs
+static const int NARROW_THREADS = 1024;
+static const uint64_t SOLVE_NONE = ~0ull;
+static const uint32_t HINT_BIT = 0x80000000u;
+
+enum StepKind { STEP_WIDE = 0, STEP_NARROW, STEP_COUNT, STEP_COMMIT };
+struct Step { int kind; uint64_t a, b; };       // WIDE: sched range [a, b); NARROW: levels [a, b); COUNT / COMMIT: hint id a
+enum SolveErr { SE_OK = 0, SE_UNSOLVED = 1, SE_DIV0 = 2, SE_INDEX = 3, SE_HINT = 4 };
+
+struct ProgView {
+    const uint64_t *ptr[3]; const uint32_t *wire[3], *coef[3];
+    const uint64_t *aux_ptr; const uint32_t *aux_wire, *aux_coef;
+    const Fr *coeffs; uint32_t one_id, minus_one_id;
+    const uint32_t *sched; const uint64_t *lvl_start;
+    const uint32_t *hint_fn, *hint_param, *hint_out, *hint_nout; const uint64_t *hint_in0, *hint_in1;
+    const uint64_t *table_ptr;
+    uint64_t *solve_e;
+    Fr *w; uint8_t *solved; unsigned long long *err;      // err: (code << 56) | row or hint id, first writer wins
+};
+
+}  // namespace zk
+
+struct zkpor_program {
+    uint64_t n_wires = 0, n_public = 0, n_secret = 0, n_rows = 0, n_instr = 0, n_levels = 0, n_hints = 0, n_aux_rows = 0, n_tables = 0;
+    zkpor_r1cs *cs = nullptr;
+    uint64_t *aux_ptr = nullptr; uint32_t *aux_wire = nullptr, *aux_coef = nullptr;
+    uint32_t *sched = nullptr; uint64_t *lvl_start = nullptr;
+    uint32_t *hint_fn = nullptr, *hint_param = nullptr, *hint_out = nullptr, *hint_nout = nullptr; uint64_t *hint_in0 = nullptr, *hint_in1 = nullptr;
+    uint64_t *table_ptr = nullptr;
+    uint64_t *solve_e = nullptr;
+    unsigned long long *err = nullptr;
+    uint32_t *counters = nullptr; uint64_t counters_cap = 0;
+    uint32_t minus_one_id = 0xFFFFFFFFu;
+    std::vector<zk::Step> steps;
+    std::vector<uint32_t> h_hint_fn, h_hint_nout, h_hint_out; std::vector<uint64_t> h_hint_in0, h_hint_in1;
+    uint64_t stats[4] = {0, 0, 0, 0};
+    bool has_commit = false;
+    zk::DevBuf wires, abc;
+};
+
+namespace zk {
+
+__device__ __forceinline__ void solve_fail(const ProgView &v, int code, uint64_t where) {
+    atomicCAS(v.err, 0ull, ((unsigned long long)code << 56) | where);
+}
+
+// one term of a linear expression: coefficient ids 1 and -1 skip the product
+__device__ __forceinline__ Fr term_acc(const ProgView &v, const Fr &acc, uint32_t cid, const Fr &x) {
+    if (cid == v.one_id) return Fr::add(acc, x);
+    if (cid == v.minus_one_id) return Fr::sub(acc, x);
+    return Fr::add(acc, Fr::mul(v.coeffs[cid], x));
+}
+
+// sum over the terms of row `row` except position `skip`, the G lanes of a group taking every G-th term; valid on lane 0
+template <int G>
+__device__ __forceinline__ Fr group_dot(const ProgView &v, const uint64_t *ptr, const uint32_t *wire, const uint32_t *coef, uint64_t row,
+                                        uint64_t skip, int lane, unsigned mask) {
+    Fr acc = Fr::zero();
+    const uint64_t e1 = ptr[row + 1];
+    for (uint64_t e = ptr[row] + lane; e < e1; e += G) {
+        if (e == skip) continue;
+        acc = term_acc(v, acc, coef[e], v.w[wire[e]]);
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.l[i] = __shfl_down_sync(mask, acc.l[i], off, G);
+        acc = Fr::add(acc, o);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ Fr aux_eval(const ProgView &v, uint64_t row) {
+    Fr acc = Fr::zero();
+    for (uint64_t e = v.aux_ptr[row], e1 = v.aux_ptr[row + 1]; e < e1; e++) acc = term_acc(v, acc, v.aux_coef[e], v.w[v.aux_wire[e]]);
+    return acc;
+}
+
+__device__ __forceinline__ bool geq256(const uint32_t *a, const uint32_t *b) {
+    for (int i = 7; i >= 0; i--) { if (a[i] > b[i]) return true; if (a[i] < b[i]) return false; }
+    return true;
+}
+
+// big.Int DivMod on canonical 256-bit values: word division for a one-word divisor, shift-subtract otherwise
+__device__ void divmod256(const uint32_t *x, const uint32_t *d, uint32_t *q, uint32_t *r) {
+    bool small = true;
+    for (int i = 1; i < 8; i++) small &= d[i] == 0;
+    if (small) {
+        uint64_t rem = 0;
+        for (int i = 7; i >= 0; i--) { uint64_t cur = (rem << 32) | x[i]; q[i] = (uint32_t)(cur / d[0]); rem = cur % d[0]; }
+        for (int i = 1; i < 8; i++) r[i] = 0;
+        r[0] = (uint32_t)rem;
+        return;
+    }
+    for (int i = 0; i < 8; i++) { q[i] = 0; r[i] = 0; }
+    for (int bit = 255; bit >= 0; bit--) {
+        for (int i = 7; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 31);
+        r[0] = (r[0] << 1) | ((x[bit >> 5] >> (bit & 31)) & 1u);
+        if (geq256(r, d)) {
+            uint64_t borrow = 0;
+            for (int i = 0; i < 8; i++) { uint64_t t = (uint64_t)r[i] - d[i] - borrow; r[i] = (uint32_t)t; borrow = (t >> 63) & 1; }
+            q[bit >> 5] |= 1u << (bit & 31);
+        }
+    }
+}
+
+__device__ __forceinline__ Fr fr_from_words(const uint32_t *p) { Fr t; for (int i = 0; i < 8; i++) t.l[i] = p[i]; return Fr::to_mont(t); }
+
+// hint functions except COUNT and COMMIT; lane 0 of the group runs them
+template <bool DRY>
+__device__ void exec_hint(const ProgView &v, uint32_t h) {
+    const uint32_t fn = v.hint_fn[h], param = v.hint_param[h], out = v.hint_out[h], n_out = v.hint_nout[h];
+    if (DRY) { for (uint32_t k = 0; k < n_out; k++) v.solved[out + k] = 1; return; }
+    const uint64_t r0 = v.hint_in0[h], r1 = v.hint_in1[h];
+    switch (fn) {
+    case ZKPOR_HINT_DIVMOD: {
+        const Fr x = Fr::from_mont(aux_eval(v, r0)), d = Fr::from_mont(aux_eval(v, r0 + 1));
+        if (d.is_zero()) { solve_fail(v, SE_DIV0, h); return; }
+        uint32_t q[8], r[8];
+        divmod256(x.l, d.l, q, r);
+        v.w[out] = fr_from_words(q); v.w[out + 1] = fr_from_words(r);
+        break;
+    }
+    case ZKPOR_HINT_NBITS: {
+        const Fr x = Fr::from_mont(aux_eval(v, r0));
+        for (uint32_t k = 0; k < n_out; k++) v.w[out + k] = (k < 256 && ((x.l[k >> 5] >> (k & 31)) & 1u)) ? Fr::one() : Fr::zero();
+        break;
+    }
+    case ZKPOR_HINT_INVZERO: v.w[out] = Fr::inv(aux_eval(v, r0)); break;
+    case ZKPOR_HINT_DECOMPOSE: {
+        const Fr x = Fr::from_mont(aux_eval(v, r0));
+        for (uint32_t k = 0; k < n_out; k++) {
+            const uint32_t lo = k * param;
+            uint64_t limb = 0;
+            if (lo < 256) {
+                limb = x.l[lo >> 5] >> (lo & 31);
+                if ((lo & 31) + param > 32 && (lo >> 5) + 1 < 8) limb |= (uint64_t)x.l[(lo >> 5) + 1] << (32 - (lo & 31));
+                limb &= (param >= 32) ? 0xFFFFFFFFull : ((1ull << param) - 1);
+            }
+            v.w[out + k] = Fr::from_u64(limb);
+        }
+        break;
+    }
+    case ZKPOR_HINT_LOOKUP: {
+        const uint64_t t0 = v.table_ptr[param], t1 = v.table_ptr[param + 1];
+        for (uint64_t r = r0; r < r1; r++) {
+            const Fr q = Fr::from_mont(aux_eval(v, r));
+            bool ok = true;
+            for (int i = 2; i < 8; i++) ok &= q.l[i] == 0;
+            const uint64_t idx = (uint64_t)q.l[0] | ((uint64_t)q.l[1] << 32);
+            if (!ok || idx >= t1 - t0) { solve_fail(v, SE_INDEX, h); return; }
+            v.w[out + (uint32_t)(r - r0)] = aux_eval(v, t0 + idx);
+        }
+        break;
+    }
+    case ZKPOR_HINT_CMP: {
+        const Fr x = Fr::from_mont(aux_eval(v, r0)), y = Fr::from_mont(aux_eval(v, r0 + 1));
+        const bool ge = geq256(x.l, y.l), le = geq256(y.l, x.l);
+        v.w[out] = (ge && le) ? Fr::zero() : (ge ? Fr::one() : Fr::neg(Fr::one()));
+        break;
+    }
+    default: solve_fail(v, SE_HINT, h);
+    }
+}
+
+// one instruction by a group of G lanes (lane = index in the group, mask = the group's lanes)
+template <int G, bool DRY>
+__device__ __forceinline__ void exec_instr(const ProgView &v, uint32_t packed, int lane, unsigned mask) {
+    if (packed & HINT_BIT) {
+        if (lane == 0) exec_hint<DRY>(v, packed & ~HINT_BIT);
+        return;
+    }
+    const uint64_t row = packed;
+    if (DRY) {
+        // the one wire of this constraint that is not solved yet
+        uint64_t cand = SOLVE_NONE; uint32_t found = 0;
+        for (int side = 0; side < 3; side++)
+            for (uint64_t e = v.ptr[side][row] + lane, e1 = v.ptr[side][row + 1]; e < e1; e += G)
+                if (!v.solved[v.wire[side][e]]) { cand = ((uint64_t)side << 62) | e; found++; }
+        uint32_t total = found;
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) total += __shfl_xor_sync(mask, total, off, G);
+        if (total > 1) { if (lane == 0) solve_fail(v, SE_UNSOLVED, row); return; }
+        if (total == 0) { if (lane == 0) v.solve_e[row] = SOLVE_NONE; return; }
+        if (found) { v.solve_e[row] = cand; v.solved[v.wire[cand >> 62][cand & ((1ull << 62) - 1)]] = 1; }
+        return;
+    }
+    const uint64_t se = v.solve_e[row];
+    if (se == SOLVE_NONE) return;                         // an assertion: checked with a, b, c after the solve
+    const int side = (int)(se >> 62);
+    const uint64_t pos = se & ((1ull << 62) - 1);
+    const Fr a = group_dot<G>(v, v.ptr[0], v.wire[0], v.coef[0], row, side == 0 ? pos : SOLVE_NONE, lane, mask);
+    const Fr b = group_dot<G>(v, v.ptr[1], v.wire[1], v.coef[1], row, side == 1 ? pos : SOLVE_NONE, lane, mask);
+    const Fr c = group_dot<G>(v, v.ptr[2], v.wire[2], v.coef[2], row, side == 2 ? pos : SOLVE_NONE, lane, mask);
+    if (lane != 0) return;
+    const uint32_t cid = v.coef[side][pos];
+    Fr num, den;
+    bool unit = false, neg = false;
+    if (side == 2) {                                      // L*R = known + cf*x
+        num = Fr::sub(Fr::mul(a, b), c);
+        unit = cid == v.one_id; neg = cid == v.minus_one_id;
+        den = v.coeffs[cid];
+    } else {                                              // (known + cf*x) * other = c
+        const Fr &known = side == 0 ? a : b, &other = side == 0 ? b : a;
+        num = Fr::sub(c, Fr::mul(known, other));
+        den = cid == v.one_id ? other : Fr::mul(v.coeffs[cid], other);
+        if (den.is_zero()) { solve_fail(v, SE_DIV0, row); return; }
+    }
+    Fr x = unit ? num : (neg ? Fr::neg(num) : Fr::mul(num, Fr::inv(den)));
+    v.w[v.wire[side][pos]] = x;
+}
+
+template <int G, bool DRY>
+__global__ void __launch_bounds__(256) k_solve_wide(ProgView v, uint64_t pos0, uint64_t count) {
+    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (g >= count) return;                               // whole groups leave together (G divides the block size)
+    const int lane = threadIdx.x & (G - 1);
+    const unsigned mask = (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << ((threadIdx.x & 31) & ~(G - 1));
+    exec_instr<G, DRY>(v, v.sched[pos0 + g], lane, mask);
+}
+
+// levels [l0, l1), each at most a few dozen instructions: one CTA, a warp per instruction, a barrier per level
+template <bool DRY>
+__global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow(ProgView v, uint64_t l0, uint64_t l1) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (uint64_t l = l0; l < l1; l++) {
+        const uint64_t s0 = v.lvl_start[l], s1 = v.lvl_start[l + 1];
+        for (uint64_t p = s0 + warp; p < s1; p += nwarps) exec_instr<32, DRY>(v, v.sched[p], lane, 0xFFFFFFFFu);
+        __syncthreads();
+    }
+}
+
+__global__ void k_count_queries(ProgView v, uint64_t r0, uint64_t r1, uint32_t n_out, uint32_t *cnt, uint32_t hint) {
+    const uint64_t r = r0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= r1) return;
+    const Fr q = Fr::from_mont(aux_eval(v, r));
+    bool ok = true;
+    for (int i = 1; i < 8; i++) ok &= q.l[i] == 0;
+    if (!ok || q.l[0] >= n_out) { solve_fail(v, SE_INDEX, hint); return; }
+    atomicAdd(cnt + q.l[0], 1u);
+}
+__global__ void k_count_store(ProgView v, const uint32_t *cnt, uint32_t out, uint32_t n_out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_out) v.w[out + k] = Fr::from_u64(cnt[k]);
+}
+__global__ void k_mark_solved(uint8_t *solved, uint64_t first, uint64_t n) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) solved[first + k] = 1;
+}
+
+__global__ void k_check_abc(const Fr *__restrict__ a, const Fr *__restrict__ b, const Fr *__restrict__ c, uint64_t n, unsigned long long *first_bad) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (Fr::mul(a[k], b[k]) != c[k]) atomicMin(first_bad, (unsigned long long)k);
+}
+
+int32_t r1cs_check_dev(zkpor_ctx *ctx, const Fr *d_a, const Fr *d_b, const Fr *d_c, uint64_t n_rows) {
+    ZK_TRY(ctx->misc.reserve(64));
+    unsigned long long *bad = ctx->misc.as<unsigned long long>();
+    ZK_CUDA(cudaMemsetAsync(bad, 0xFF, 8, ctx->stream));
+    ZK_LAUNCH(ctx, k_check_abc, grid_for(n_rows, 256), 256, 0, d_a, d_b, d_c, n_rows, bad);
+    unsigned long long h = 0;
+    ZK_CUDA(cudaMemcpyAsync(&h, bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h != ~0ull) { set_error("solve: constraint #%llu is not satisfied", h); return ZKPOR_ERR_STATE; }
+    return ZKPOR_OK;
+}
+
+static ProgView make_view(zkpor_program *p, Fr *w, uint8_t *solved) {
+    ProgView v;
+    for (int m = 0; m < 3; m++) { v.ptr[m] = p->cs->row_ptr[m]; v.wire[m] = p->cs->wire_ids[m]; v.coef[m] = p->cs->coeff_ids[m]; }
+    v.aux_ptr = p->aux_ptr; v.aux_wire = p->aux_wire; v.aux_coef = p->aux_coef;
+    v.coeffs = p->cs->coeffs; v.one_id = p->cs->one_id; v.minus_one_id = p->minus_one_id;
+    v.sched = p->sched; v.lvl_start = p->lvl_start;
+    v.hint_fn = p->hint_fn; v.hint_param = p->hint_param; v.hint_out = p->hint_out; v.hint_nout = p->hint_nout; v.hint_in0 = p->hint_in0; v.hint_in1 = p->hint_in1;
+    v.table_ptr = p->table_ptr; v.solve_e = p->solve_e; v.w = w; v.solved = solved; v.err = p->err;
+    return v;
+}
+
+static int32_t solve_error(zkpor_program *p, zkpor_ctx *ctx, const char *what) {
+    unsigned long long e = 0;
+    ZK_CUDA(cudaMemcpyAsync(&e, p->err, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (e == 0) return ZKPOR_OK;
+    const int code = (int)(e >> 56); const unsigned long long where = e & ((1ull << 56) - 1);
+    const char *msg = code == SE_UNSOLVED ? "constraint has more than one unsolved wire (levels are not a valid schedule)"
+                    : code == SE_DIV0 ? "division by zero" : code == SE_INDEX ? "lookup / multiplicity index outside its table" : "unknown hint function";
+    set_error("%s: %s (constraint row or hint record #%llu)", what, msg, where);
+    return ZKPOR_ERR_STATE;
+}
+
+// runs the schedule: DRY = find every R1C instruction's unknown on solved-flags, else solve
+template <bool DRY>
+static int32_t run_schedule(zkpor_ctx *ctx, zkpor_program *p, zkpor_pk *pk, Fr *w, uint8_t *solved, G1XYZZ *commit, G1XYZZ *pok) {
+    ProgView v = make_view(p, w, solved);
+    ZK_CUDA(cudaMemsetAsync(p->err, 0, 8, ctx->stream));
+    for (const Step &s : p->steps) {
+        switch (s.kind) {
+        case STEP_WIDE: {
+            const uint64_t count = s.b - s.a;
+            ZK_LAUNCH(ctx, (k_solve_wide<8, DRY>), grid_for(count * 8, 256), 256, 0, v, s.a, count);
+            break;
+        }
+        case STEP_NARROW:
+            ZK_LAUNCH(ctx, k_solve_narrow<DRY>, 1, NARROW_THREADS, 0, v, s.a, s.b);
+            break;
+        case STEP_COUNT: {
+            const uint32_t h = (uint32_t)s.a, n_out = p->h_hint_nout[h], out = p->h_hint_out[h];
+            if (DRY) { ZK_LAUNCH(ctx, k_mark_solved, grid_for(n_out, 256), 256, 0, solved, (uint64_t)out, (uint64_t)n_out); break; }
+            const uint64_t r0 = p->h_hint_in0[h], r1 = p->h_hint_in1[h];
+            ZK_CUDA(cudaMemsetAsync(p->counters, 0, (size_t)n_out * 4, ctx->stream));
+            if (r1 > r0) ZK_LAUNCH(ctx, k_count_queries, grid_for(r1 - r0, 256), 256, 0, v, r0, r1, n_out, p->counters, h);
+            ZK_LAUNCH(ctx, k_count_store, grid_for(n_out, 256), 256, 0, v, (const uint32_t *)p->counters, out, n_out);
+            break;
+        }
+        case STEP_COMMIT: {
+            const uint32_t h = (uint32_t)s.a, out = p->h_hint_out[h];
+            if (DRY) { ZK_LAUNCH(ctx, k_mark_solved, grid_for(1, 32), 32, 0, solved, (uint64_t)out, (uint64_t)1); break; }
+            // Prove's override of the BSB22 placeholder: Pedersen-commit the private committed wires, hash the
+            // commitment to the field; the proof of knowledge shares the sort of the committed values, so it is taken here as well
+            if (pk == nullptr || !pk->has_commitment) { set_error("solve: the program has a commitment hint but no proving key with a commitment key was given"); return ZKPOR_ERR_INVALID_ARG; }
+            ZK_TRY(pk_commit_and_pok(ctx, pk, w, commit, pok));
+            const Fr ch = commitment_challenge_g1(commit->to_affine());
+            ZK_CUDA(cudaMemcpyAsync(w + out, &ch, 32, cudaMemcpyHostToDevice, ctx->stream));
+            ZK_CUDA(cudaStreamSynchronize(ctx->stream));   // `ch` lives on this frame
+            break;
+        }
+        }
+    }
+    return solve_error(p, ctx, DRY ? "program_upload" : "solve");
+}
+
+int32_t solver_run(zkpor_ctx *ctx, zkpor_program *prog, zkpor_pk *pk, Fr *d_wires, G1XYZZ *commit, G1XYZZ *pok, bool *has_commit) {
+    *has_commit = prog->has_commit;
+    return run_schedule<false>(ctx, prog, pk, d_wires, nullptr, commit, pok);
+}
+zkpor_r1cs *program_matrices(zkpor_program *prog) { return prog->cs; }
+uint64_t program_inputs(const zkpor_program *prog) { return prog->n_public - 1 + prog->n_secret; }
+
+// host copy of an array that may live on either side
+template <class T>
+static int32_t fetch(std::vector<T> &dst, const T *src, size_t n) {
+    dst.resize(n);
+    if (n) ZK_CUDA(cudaMemcpy(dst.data(), src, n * sizeof(T), cudaMemcpyDefault));
+    return ZKPOR_OK;
+}
+template <class T>
+static int32_t put(T **dst, const T *src, size_t n) {
+    *dst = nullptr;
+    ZK_CUDA(cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) ZK_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyDefault));
+    return ZKPOR_OK;
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+extern "C" {
+
+int32_t zkpor_program_free(zkpor_ctx *ctx, zkpor_program *p) {
+    if (!p) return ZKPOR_OK;
+    if (p->cs) zkpor_r1cs_free(ctx, p->cs);
+    void *ptrs[] = {p->aux_ptr, p->aux_wire, p->aux_coef, p->sched, p->lvl_start, p->hint_fn, p->hint_param, p->hint_out, p->hint_nout,
+                    p->hint_in0, p->hint_in1, p->table_ptr, p->solve_e, p->err, p->counters};
+    for (void *q : ptrs) if (q) cudaFree(q);
+    p->wires.release(); p->abc.release();
+    delete p;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_program_stats(zkpor_program *prog, uint64_t out4[4]) {
+    ZK_REQUIRE(prog && out4, "program_stats: null argument");
+    for (int i = 0; i < 4; i++) out4[i] = prog->stats[i];
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_program **out) {
+    ZK_REQUIRE(ctx && d && out, "program_upload: null argument");
+    ZK_REQUIRE(d->n_public >= 1 && d->n_public + d->n_secret <= d->n_wires && d->n_wires < (1ull << 32), "program_upload: wire counts out of range");
+    ZK_REQUIRE(d->n_instr > 0 && d->n_instr < (1ull << 32) && d->n_constraints < (1ull << 31) && d->n_hints < (1ull << 31), "program_upload: sizes out of range");
+    ZK_REQUIRE(d->instr_kind && d->instr_arg && d->level_ptr && d->level_instr, "program_upload: null instruction arrays");
+    ZK_REQUIRE(d->n_hints == 0 || (d->hint_fn && d->hint_param && d->hint_out_first && d->hint_n_out && d->hint_in_ptr && d->hint_in_end), "program_upload: null hint arrays");
+    ZK_REQUIRE(d->n_aux_rows == 0 || d->aux.row_ptr, "program_upload: null auxiliary matrix");
+    ZK_REQUIRE(d->n_tables == 0 || d->table_ptr, "program_upload: null table_ptr");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    *out = nullptr;
+    zkpor_program *p = new zkpor_program();
+    p->n_wires = d->n_wires; p->n_public = d->n_public; p->n_secret = d->n_secret; p->n_rows = d->n_constraints; p->n_instr = d->n_instr;
+    p->n_levels = d->n_levels; p->n_hints = d->n_hints; p->n_aux_rows = d->n_aux_rows; p->n_tables = d->n_tables;
+    int32_t rc = zkpor_r1cs_upload(ctx, d->n_constraints, d->n_wires, &d->l, &d->r, &d->o, d->coeff_table, d->n_coeffs, &p->cs);
+    auto fail = [&](int32_t code) { zkpor_program_free(ctx, p); return code; };
+    if (rc != ZKPOR_OK) return fail(rc);
+    // the coefficient -1, like 1, skips the product
+    {
+        std::vector<Fr> tab;
+        if ((rc = fetch(tab, (const Fr *)d->coeff_table, d->n_coeffs)) != ZKPOR_OK) return fail(rc);
+        const Fr one = Fr::one(), m1 = Fr::neg(Fr::one());
+        for (uint64_t i = 0; i < d->n_coeffs; i++) {
+            if (tab[i] == m1 && p->minus_one_id == 0xFFFFFFFFu) p->minus_one_id = (uint32_t)i;
+            if (tab[i] == one && p->cs->one_id == 0xFFFFFFFFu) p->cs->one_id = (uint32_t)i;
+        }
+    }
+    // instruction-level arrays come to the host (O(instructions)); the matrices (O(terms)) never do
+    std::vector<uint8_t> kind; std::vector<uint32_t> arg, lvl_instr, hparam; std::vector<uint64_t> lvl_ptr, tptr;
+    if ((rc = fetch(kind, d->instr_kind, d->n_instr)) != ZKPOR_OK || (rc = fetch(arg, d->instr_arg, d->n_instr)) != ZKPOR_OK ||
+        (rc = fetch(lvl_instr, d->level_instr, d->n_instr)) != ZKPOR_OK || (rc = fetch(lvl_ptr, d->level_ptr, d->n_levels + 1)) != ZKPOR_OK ||
+        (rc = fetch(p->h_hint_fn, d->hint_fn, d->n_hints)) != ZKPOR_OK || (rc = fetch(p->h_hint_nout, d->hint_n_out, d->n_hints)) != ZKPOR_OK ||
+        (rc = fetch(p->h_hint_out, d->hint_out_first, d->n_hints)) != ZKPOR_OK || (rc = fetch(p->h_hint_in0, d->hint_in_ptr, d->n_hints)) != ZKPOR_OK ||
+        (rc = fetch(p->h_hint_in1, d->hint_in_end, d->n_hints)) != ZKPOR_OK || (rc = fetch(hparam, d->hint_param, d->n_hints)) != ZKPOR_OK ||
+        (rc = fetch(tptr, d->table_ptr, d->n_tables ? d->n_tables + 1 : 0)) != ZKPOR_OK)
+        return fail(rc);
+    auto bad = [&](const char *m) { set_error("program_upload: %s", m); return fail(ZKPOR_ERR_INVALID_ARG); };
+    if (lvl_ptr[0] != 0 || lvl_ptr[d->n_levels] != d->n_instr) return bad("level_ptr does not span the instructions");
+    uint64_t max_out = 1;
+    for (uint64_t h = 0; h < d->n_hints; h++) {
+        if ((uint64_t)p->h_hint_out[h] + p->h_hint_nout[h] > d->n_wires) return bad("hint outputs out of range");
+        if (p->h_hint_in0[h] > p->h_hint_in1[h] || p->h_hint_in1[h] > d->n_aux_rows) return bad("hint inputs out of range");
+        const uint32_t fn = p->h_hint_fn[h];
+        if (fn < ZKPOR_HINT_DIVMOD || fn > ZKPOR_HINT_COMMIT) return bad("unknown hint function id");
+        if ((fn == ZKPOR_HINT_DIVMOD || fn == ZKPOR_HINT_CMP) && (p->h_hint_in1[h] - p->h_hint_in0[h] != 2 || p->h_hint_nout[h] != (fn == ZKPOR_HINT_DIVMOD ? 2u : 1u))) return bad("DIVMOD / CMP hint arity");
+        if ((fn == ZKPOR_HINT_NBITS || fn == ZKPOR_HINT_DECOMPOSE || fn == ZKPOR_HINT_INVZERO) && p->h_hint_in1[h] - p->h_hint_in0[h] != 1) return bad("single-input hint arity");
+        if (fn == ZKPOR_HINT_DECOMPOSE && (hparam[h] == 0 || hparam[h] > 32)) return bad("DECOMPOSE limb width must be 1..32 bits");
+        if (fn == ZKPOR_HINT_LOOKUP && (hparam[h] >= d->n_tables || p->h_hint_in1[h] - p->h_hint_in0[h] != p->h_hint_nout[h])) return bad("LOOKUP table id / arity");
+        if (fn == ZKPOR_HINT_COUNT) max_out = std::max<uint64_t>(max_out, p->h_hint_nout[h]);
+        if (fn == ZKPOR_HINT_COMMIT) { if (p->h_hint_nout[h] != 1) return bad("COMMIT hint has one output"); p->has_commit = true; }
+    }
+    for (uint64_t t = 0; t < d->n_tables; t++) if (tptr[t] > tptr[t + 1] || tptr[t + 1] > d->n_aux_rows) return bad("table_ptr out of range");
+    // schedule: instructions in level order, special hints lifted out as steps of their own
+    std::vector<uint32_t> sched; sched.reserve(d->n_instr);
+    std::vector<uint64_t> lvl_start; lvl_start.reserve(d->n_levels + 1);
+    int64_t run_first = -1;
+    auto close_run = [&](uint64_t end_level) {
+        if (run_first >= 0) { p->steps.push_back({STEP_NARROW, (uint64_t)run_first, end_level}); p->stats[1]++; p->stats[2] += end_level - run_first; run_first = -1; }
+    };
+    for (uint64_t l = 0; l < d->n_levels; l++) {
+        lvl_start.push_back(sched.size());
+        bool special = false;
+        for (uint64_t q = lvl_ptr[l]; q < lvl_ptr[l + 1]; q++) {
+            const uint32_t ins = lvl_instr[q];
+            if (ins >= d->n_instr) return bad("level_instr out of range");
+            if (kind[ins] == ZKPOR_INS_R1C) { if (arg[ins] >= d->n_constraints) return bad("instruction row out of range"); sched.push_back(arg[ins]); continue; }
+            if (kind[ins] != ZKPOR_INS_HINT || arg[ins] >= d->n_hints) return bad("instruction kind / hint id out of range");
+            const uint32_t fn = p->h_hint_fn[arg[ins]];
+            if (fn == ZKPOR_HINT_COUNT || fn == ZKPOR_HINT_COMMIT) {
+                if (!special) close_run(l);
+                special = true;
+                p->steps.push_back({fn == ZKPOR_HINT_COUNT ? STEP_COUNT : STEP_COMMIT, arg[ins], 0});
+                if (fn == ZKPOR_HINT_COUNT) p->stats[3]++;
+            } else sched.push_back(arg[ins] | HINT_BIT);
+        }
+        const uint64_t n_l = sched.size() - lvl_start.back();
+        if (n_l == 0) continue;
+        if (n_l <= NARROW_MAX) { if (run_first < 0) run_first = (int64_t)l; }
+        else { close_run(l); p->steps.push_back({STEP_WIDE, lvl_start.back(), (uint64_t)sched.size()}); p->stats[0]++; }
+    }
+    lvl_start.push_back(sched.size());
+    close_run(d->n_levels);
+    // device copies
+    if ((rc = put(&p->sched, sched.data(), sched.size())) != ZKPOR_OK || (rc = put(&p->lvl_start, lvl_start.data(), lvl_start.size())) != ZKPOR_OK ||
+        (rc = put(&p->hint_fn, d->hint_fn, d->n_hints)) != ZKPOR_OK || (rc = put(&p->hint_param, d->hint_param, d->n_hints)) != ZKPOR_OK ||
+        (rc = put(&p->hint_out, d->hint_out_first, d->n_hints)) != ZKPOR_OK || (rc = put(&p->hint_nout, d->hint_n_out, d->n_hints)) != ZKPOR_OK ||
+        (rc = put(&p->hint_in0, d->hint_in_ptr, d->n_hints)) != ZKPOR_OK || (rc = put(&p->hint_in1, d->hint_in_end, d->n_hints)) != ZKPOR_OK ||
+        (rc = put(&p->table_ptr, tptr.data(), tptr.size())) != ZKPOR_OK ||
+        (rc = put(&p->aux_ptr, d->aux.row_ptr, d->n_aux_rows + 1)) != ZKPOR_OK || (rc = put(&p->aux_wire, d->aux.wire_ids, d->aux.nnz)) != ZKPOR_OK ||
+        (rc = put(&p->aux_coef, d->aux.coeff_ids, d->aux.nnz)) != ZKPOR_OK)
+        return fail(rc);
+    p->counters_cap = max_out;
+    if (cudaMalloc((void **)&p->solve_e, std::max<uint64_t>(d->n_constraints, 1) * 8) != cudaSuccess || cudaMalloc((void **)&p->err, 8) != cudaSuccess ||
+        cudaMalloc((void **)&p->counters, max_out * 4) != cudaSuccess) { set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
+    // dry run: which wire does every R1C instruction solve for
+    uint8_t *solved = nullptr;
+    if (cudaMalloc((void **)&solved, d->n_wires) != cudaSuccess) { set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
+    cudaMemsetAsync(solved, 0, d->n_wires, ctx->stream);
+    cudaMemsetAsync(solved, 1, d->n_public + d->n_secret, ctx->stream);
+    cudaMemsetAsync(p->solve_e, 0xFF, std::max<uint64_t>(d->n_constraints, 1) * 8, ctx->stream);
+    rc = run_schedule<true>(ctx, p, nullptr, nullptr, solved, nullptr, nullptr);
+    if (rc == ZKPOR_OK) {
+        // every wire must have been reached
+        std::vector<uint8_t> hs;
+        rc = fetch(hs, (const uint8_t *)solved, d->n_wires);
+        if (rc == ZKPOR_OK)
+            for (uint64_t i = 0; i < d->n_wires; i++)
+                if (!hs[i]) { set_error("program_upload: wire %llu is never solved by the schedule", (unsigned long long)i); rc = ZKPOR_ERR_INVALID_ARG; break; }
+    }
+    cudaFree(solved);
+    if (rc != ZKPOR_OK) return fail(rc);
+    *out = p;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_r1cs_solve(zkpor_ctx *ctx, zkpor_program *prog, zkpor_pk *pk, const void *inputs, void *out_wires, void *out_a, void *out_b,
+                         void *out_c, void *out_commitment64) {
+    ZK_REQUIRE(ctx && prog && inputs, "r1cs_solve: null argument");
+    ZK_REQUIRE(!pk || pk->n_wires == prog->n_wires, "r1cs_solve: the program and the key disagree on the number of wires");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    stages_reset(ctx);
+    Fr *w;
+    if (out_wires && is_device_ptr(out_wires)) w = (Fr *)out_wires;
+    else { ZK_TRY(prog->wires.reserve(prog->n_wires * 32)); w = prog->wires.as<Fr>(); }
+    const Fr one = Fr::one();
+    stage_begin(ctx, ST_H2D);
+    ZK_CUDA(cudaMemcpyAsync(w, &one, 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(w + 1, inputs, program_inputs(prog) * 32, cudaMemcpyDefault, ctx->stream));
+    stage_end(ctx, ST_H2D);
+    stage_begin(ctx, ST_SOLVE);
+    G1XYZZ commit = G1XYZZ::inf(), pok = G1XYZZ::inf();
+    bool has_commit = false;
+    ZK_TRY(solver_run(ctx, prog, pk, w, &commit, &pok, &has_commit));
+    // a = L w, b = R w, c = O w and gnark's satisfaction check
+    const size_t bytes = prog->n_rows * sizeof(Fr);
+    void *outs[3] = {out_a, out_b, out_c};
+    Fr *d[3];
+    bool need_tmp = false;
+    for (int m = 0; m < 3; m++) need_tmp |= !(outs[m] && is_device_ptr(outs[m]));
+    if (need_tmp) ZK_TRY(prog->abc.reserve(3 * bytes));
+    for (int m = 0; m < 3; m++) d[m] = (outs[m] && is_device_ptr(outs[m])) ? (Fr *)outs[m] : prog->abc.as<Fr>() + (size_t)m * prog->n_rows;
+    ZK_TRY(r1cs_eval_dev(ctx, prog->cs, w, d[0], d[1], d[2]));
+    ZK_TRY(r1cs_check_dev(ctx, d[0], d[1], d[2], prog->n_rows));
+    stage_end(ctx, ST_SOLVE);
+    stage_begin(ctx, ST_D2H);
+    for (int m = 0; m < 3; m++)
+        if (outs[m] && !is_device_ptr(outs[m])) ZK_CUDA(cudaMemcpyAsync(outs[m], d[m], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_wires && !is_device_ptr(out_wires)) ZK_CUDA(cudaMemcpyAsync(out_wires, w, prog->n_wires * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    stage_end(ctx, ST_D2H);
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out_commitment64) {
+        const G1Affine c = has_commit ? commit.to_affine() : G1Affine::inf();
+        memcpy(out_commitment64, &c, 64);
+    }
+    stages_collect(ctx);
+    return ZKPOR_OK;
+}
+
+}  // extern "C"
