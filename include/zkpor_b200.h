@@ -58,7 +58,8 @@ int32_t zkpor_ctx_last_timings(zkpor_ctx *ctx, float *out_ms, int32_t cap, int32
 const char *zkpor_stage_name(int32_t i);
 /* Per-launch timing of the dominant kernels (CUDA events on the context's stream around every launch of a class):
  * enable, run, then query.  klass: 0 = G1 bucket accumulation, 1 = G2 bucket accumulation, 2 = NTT butterfly pass,
- * 3 = digit/scatter (sort) kernels, 4 = Poseidon/Merkle kernels.  units = terms (MSM), elements (NTT), hashes. */
+ * 3 = digit/scatter (sort) kernels, 4 = Poseidon/Merkle kernels, 5 = solver wide-level launches, 6 = solver fused narrow runs.
+ * units = terms (MSM), elements (NTT), hashes, instructions (5), levels (6). */
 int32_t zkpor_ctx_kernel_timing(zkpor_ctx *ctx, int32_t enable);
 int32_t zkpor_ctx_kernel_stats(zkpor_ctx *ctx, int32_t klass, double *total_ms, uint64_t *launches, uint64_t *units);
 
@@ -213,6 +214,38 @@ int32_t zkpor_r1cs_solve(zkpor_ctx *ctx, zkpor_program *prog, zkpor_pk *pk, cons
  * commitment and its proof of knowledge are computed once, mid-solve. */
 int32_t zkpor_groth16_prove_solve(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_program *prog, const void *inputs, const uint8_t r_be[32],
                                   const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len);
+
+/* ---- one proof across the N GPUs of a box -----------------------------------------------------------------
+ * The reference scales out with independent prover processes (README.md:126: several provers pull batches from one queue); this
+ * adds latency scaling of ONE proof: the key is split by point chunk (wires in N contiguous ranges, Z and the commitment basis in N
+ * chunks), computeH runs as a four-step transform with all-to-all exchanges, and the ranks' partial sums meet in one all-gather.
+ * Every rank holds the constraint system and solves the whole witness (the solver is a latency chain), so no wire data is exchanged.
+ * Two ways to form a group of N = 1, 2, 4 or 8 contexts:
+ *   - one process per GPU (torchrun, or N prover processes): rank 0 calls zkpor_comm_unique_id and passes the 128 bytes to the other
+ *     ranks by any channel; every rank calls zkpor_ctx_comm_init on its own context.  Exchanges run over NCCL (libnccl.so.2 is
+ *     resolved at run time; ZKPOR_NCCL_LIB overrides the path).
+ *   - one process (a Go prover with one OS-locked goroutine per GPU): zkpor_ctx_create_multi returns the N contexts already joined;
+ *     peers pull over NVLink with cudaMemcpyPeerAsync.  Device ids may repeat (the N-rank algorithm on fewer GPUs, for tests).
+ * On a context that belongs to a group, zkpor_pk_upload_shard uploads this rank's part of the key, and zkpor_groth16_prove_solve /
+ * zkpor_groth16_prove_wires / zkpor_r1cs_solve with such a key are COLLECTIVE: every rank calls them with the same arguments
+ * (each from its own thread or process) and every rank receives the same proof bytes -- identical to the single-GPU proof. */
+int32_t zkpor_comm_unique_id(uint8_t out_id128[128]);
+int32_t zkpor_ctx_comm_init(zkpor_ctx *ctx, const uint8_t id128[128], int32_t rank, int32_t world);
+int32_t zkpor_ctx_create_multi(const int32_t *device_ids, int32_t n, zkpor_ctx **out_ctxs /* n */);
+/* rank and size of the context's group (0 and 1 without one); out_stats (may be NULL) = all-to-all exchanges so far and the bytes
+ * this rank received from its peers in them */
+int32_t zkpor_ctx_comm_info(zkpor_ctx *ctx, int32_t *out_rank, int32_t *out_world, uint64_t out_stats[2]);
+/* desc describes the WHOLE key (host or device arrays, as for zkpor_pk_upload); only this rank's chunks are copied to its GPU */
+int32_t zkpor_pk_upload_shard(zkpor_ctx *ctx, const zkpor_pk_desc *desc, zkpor_pk **out);
+/* shard of a key: rank, world, first wire, wires, then the lengths of its A, B, K and Z chunks */
+int32_t zkpor_pk_shard_info(zkpor_pk *pk, uint64_t out8[8]);
+/* computeH across the group (collective): a, b, c = this rank's n/N evaluation rows rank, rank + N, rank + 2N, ... (zero beyond
+ * the constraint count); out_h_chunk = elements [rank n/N, (rank+1) n/N) of zkpor_compute_h's output */
+int32_t zkpor_compute_h_sharded(zkpor_ctx *ctx, const void *a, const void *b, const void *c, uint32_t log_n, void *out_h_chunk);
+/* convenience for the one-process form: runs zkpor_groth16_prove_solve on the n contexts from n host threads and returns rank 0's
+ * proof (pks[i] / progs[i] live on ctxs[i]; inputs, r, s as for zkpor_groth16_prove_solve) */
+int32_t zkpor_multi_prove_solve(zkpor_ctx **ctxs, zkpor_pk **pks, zkpor_program **progs, int32_t n, const void *inputs,
+                                const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len);
 
 /* ---- pairing / groth16.Verify --------------------------------------------------------------
  * Replaces gnark-crypto bn254.MillerLoop / FinalExponentiation / PairingCheck (ecc/bn254/pairing.go, out of tree) under

@@ -1,0 +1,58 @@
+"""Witness-solver timing on one B200 (development tool): builds the bench circuit at 2^LOG_N and times zkpor_r1cs_solve alone for a
+few schedule settings (env knobs of csrc/solver.cu), with the per-class launch statistics of the library.
+Usage: python tools/solver_bench.py [log_n] [settings...]   setting = NARROW_MAX:NARROW_THREADS:WIDE_G32_MAX"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import bench
+import zkpor_b200 as zk
+
+
+def main():
+    log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 22
+    settings = sys.argv[2:] or ["96:1024:32768", "96:512:32768", "96:1024:0", "32:1024:32768", "512:1024:32768"]
+    ctx = zk.Context(0)
+    wl = bench.Workload(torch, zk, ctx, log_n)
+    print(wl.describe(), "setup %.1f s" % wl.setup_s, flush=True)
+    wires = bench.dev_buf(torch, wl.sh["W"] * 32)
+    out = []
+    for st in settings:
+        nm, nt, g32 = st.split(":")
+        os.environ["ZKPOR_NARROW_MAX"], os.environ["ZKPOR_NARROW_THREADS"], os.environ["ZKPOR_WIDE_G32_MAX"] = nm, nt, g32
+        t0 = time.perf_counter()
+        prog = zk.Program(ctx, wl.flat)
+        up = time.perf_counter() - t0
+        for _ in range(2):
+            prog.solve_device(wl.inputs, wires, wl.pk)
+        ctx.kernel_timing(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream = torch.cuda.ExternalStream(ctx.stream())
+        torch.cuda.synchronize()
+        e0.record(stream)
+        n = 3
+        for _ in range(n):
+            prog.solve_device(wl.inputs, wires, wl.pk)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wide, narrow = ctx.kernel_stats(5), ctx.kernel_stats(6)
+        ctx.kernel_timing(False)
+        rec = dict(setting=st, upload_s=up, solve_ms=e0.elapsed_time(e1) / n, stats=prog.stats(), stage=ctx.last_timings().get("solve"),
+                   wide_ms=wide["total_ms"] / n, wide_launches=wide["launches"] // n, narrow_ms=narrow["total_ms"] / n, narrow_levels=narrow["units"] // n)
+        rec["us_per_wide_level"] = 1e3 * rec["wide_ms"] / max(1, rec["wide_launches"])
+        rec["us_per_narrow_level"] = 1e3 * rec["narrow_ms"] / max(1, rec["narrow_levels"])
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+        prog.close()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(dict(workload=wl.describe(), runs=out), open(os.path.join(ROOT, "gpurun_out", f"solver_bench_{log_n}.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -137,10 +137,34 @@ def be32(v: int) -> bytes:
 class Context:
     """One GPU, one stream, NOT re-entrant (mirrors: one proof in flight per prover process, prover.go:141-247)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _handle=None):
         self._h = C.c_void_p()
-        _check(lib().zkpor_ctx_create(C.c_int32(device), C.byref(self._h)))
+        if _handle is not None:
+            self._h = C.c_void_p(_handle)
+        else:
+            _check(lib().zkpor_ctx_create(C.c_int32(device), C.byref(self._h)))
         self.device = device
+
+    # --- one proof across N GPUs (include/zkpor_b200.h "one proof across the N GPUs of a box")
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """join an NCCL group (one process per GPU); unique_id = comm_unique_id() of rank 0, passed to every rank"""
+        assert len(unique_id) == 128
+        idb = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().zkpor_ctx_comm_init(self._h, idb, C.c_int32(rank), C.c_int32(world)))
+
+    def comm_info(self) -> dict:
+        r, w = C.c_int32(0), C.c_int32(1)
+        st = (C.c_uint64 * 2)()
+        _check(lib().zkpor_ctx_comm_info(self._h, C.byref(r), C.byref(w), st))
+        return dict(rank=r.value, world=w.value, all_to_all_calls=int(st[0]), all_to_all_bytes=int(st[1]))
+
+    def compute_h_sharded(self, a, b, c, log_n: int, out=None):
+        """collective: a, b, c = this rank's cyclic rows; returns this rank's contiguous chunk of h"""
+        w = self.comm_info()["world"]
+        if out is None:
+            out = np.zeros(((1 << log_n) // w, 4), dtype=np.uint64)
+        _check(lib().zkpor_compute_h_sharded(self._h, _ptr(a), _ptr(b), _ptr(c), C.c_uint32(log_n), _ptr(out)))
+        return out
 
     def close(self):
         if self._h:
@@ -412,7 +436,9 @@ class ProvingKey:
 
     def __init__(self, ctx: Context, *, log_n, A, B1, K, Z, B2, alpha1, beta1, delta1, beta2, delta2, n_a, n_b, n_k, n_z,
                  infinity_a=None, infinity_b=None, n_public=0, ck_basis=None, ck_basis_exp_sigma=None, private_committed=None,
-                 commitment_index=0):
+                 commitment_index=0, shard=False):
+        """shard=True: the arguments describe the WHOLE key; only the chunks of ctx's rank in its group are uploaded
+        (zkpor_pk_upload_shard) and the prove calls become collective."""
         self.ctx = ctx
         d = PkDesc()
         keep = []
@@ -445,7 +471,12 @@ class ProvingKey:
         self.has_commitment = ck_basis is not None
         self.log_n, self.n_z = log_n, n_z
         self._h = C.c_void_p()
-        _check(lib().zkpor_pk_upload(ctx._h, C.byref(d), C.byref(self._h)))
+        _check((lib().zkpor_pk_upload_shard if shard else lib().zkpor_pk_upload)(ctx._h, C.byref(d), C.byref(self._h)))
+
+    def shard_info(self) -> dict:
+        out = (C.c_uint64 * 8)()
+        _check(lib().zkpor_pk_shard_info(self._h, out))
+        return dict(zip(("rank", "world", "wire_first", "n_wires", "n_a", "n_b", "n_k", "n_z"), (int(x) for x in out)))
 
     def close(self):
         if self._h:
@@ -773,6 +804,56 @@ class VerifyingKey:
 
 
 # ----------------------------------------------------------------------------------------------- multi-GPU host logic
+def comm_unique_id() -> bytes:
+    """NCCL unique id for Context.comm_init (rank 0 creates it, every rank receives it by any channel)"""
+    out = (C.c_uint8 * 128)()
+    _check(lib().zkpor_comm_unique_id(out))
+    return bytes(out)
+
+
+def create_multi(device_ids) -> list:
+    """zkpor_ctx_create_multi: len(device_ids) contexts joined in one in-process group (drive each from its own thread)"""
+    n = len(device_ids)
+    ids = (C.c_int32 * n)(*device_ids)
+    hs = (C.c_void_p * n)()
+    _check(lib().zkpor_ctx_create_multi(ids, C.c_int32(n), hs))
+    return [Context(device_ids[i], _handle=hs[i]) for i in range(n)]
+
+
+def multi_prove_solve(ctxs, pks, progs, inputs, r: int, s: int) -> bytes:
+    """zkpor_multi_prove_solve: one proof across the group's GPUs, one host thread per context inside the library"""
+    n = len(ctxs)
+    out = np.zeros(388, dtype=np.uint8)
+    ln = C.c_uint32(0)
+    _check(lib().zkpor_multi_prove_solve((C.c_void_p * n)(*[c._h.value for c in ctxs]), (C.c_void_p * n)(*[p._h.value for p in pks]),
+                                         (C.c_void_p * n)(*[p._h.value for p in progs]), C.c_int32(n), _ptr(inputs), _be_arr(r), _be_arr(s),
+                                         _ptr(out), C.byref(ln)))
+    return out[:ln.value].tobytes()
+
+
+def run_ranks(fn, n: int) -> list:
+    """fn(rank) on n host threads (ctypes calls release the GIL, so collective library calls proceed concurrently); re-raises the
+    first failure"""
+    import threading
+    res, errs = [None] * n, [None] * n
+
+    def work(i):
+        try:
+            res[i] = fn(i)
+        except BaseException as e:   # noqa: BLE001
+            errs[i] = e
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in errs:
+        if e is not None:
+            raise e
+    return res
+
+
 def chunk_bounds(length: int, rank: int, world: int):
     """Point-chunk sharding of one key array: rank r owns [r*L/N, (r+1)*L/N)."""
     return (length * rank) // world, (length * (rank + 1)) // world

@@ -38,7 +38,7 @@ const char *get_error();
 enum Stage { ST_H2D = 0, ST_DIGITS, ST_SORT, ST_ACCUM, ST_REDUCE, ST_NTT, ST_POSEIDON, ST_D2H, ST_SOLVE, ST_COUNT };
 
 // kernel classes whose individual launches are timed with CUDA events (zkpor_ctx_kernel_stats; bench.py's roofline)
-enum KClass { KC_ACCUM_G1 = 0, KC_ACCUM_G2, KC_NTT_PASS, KC_SORT, KC_POSEIDON, KC_COUNT };
+enum KClass { KC_ACCUM_G1 = 0, KC_ACCUM_G2, KC_NTT_PASS, KC_SORT, KC_POSEIDON, KC_SOLVE_WIDE, KC_SOLVE_NARROW, KC_COUNT };
 struct KRec { int klass; uint64_t units; cudaEvent_t e0, e1; };
 
 // A grow-only device allocation reused across calls (cudaMalloc is far too slow for the hot path).
@@ -71,7 +71,7 @@ struct zkpor_ctx {
     uint64_t launches = 0;
     int poseidon_out_lane = 1;
     // scratch
-    zk::DevBuf in_points, in_scalars, sort_idx, sort_idx2, view_cnt, view_order, part_buf, part_meta, bucket_cnt, bucket_off, bucket_cur, buckets, partials, windows, misc, ntt_a, ntt_b, ntt_c, io, heavy, heavy_part, order, tree_a, tree_b, tree_meta;
+    zk::DevBuf in_points, in_scalars, sort_idx, sort_idx2, view_cnt, view_order, part_buf, part_meta, bucket_cnt, bucket_off, bucket_cur, buckets, partials, windows, misc, ntt_a, ntt_b, ntt_c, io, heavy, heavy_part, order, tree_a, tree_b, tree_meta, dist_tmp;
     bool g2_tight_regs = true;   // env ZKPOR_G2_TIGHT=0: G2 affine rounds at 170 registers / 8 warps per SM instead of 128 / 16
     bool direct_scatter = false;   // env ZKPOR_DIRECT_SCATTER=1: one-level counting sort (returning L2 atomics) at every size
     int affine_rounds = 0;    // affine tree rounds of an MSM: 0 = XYZZ only (default), -1 = automatic depth, k > 0 = at most k; env ZKPOR_AFFINE_ROUNDS
@@ -80,6 +80,9 @@ struct zkpor_ctx {
     void *pos_consts = nullptr;
     // ntt twiddles cache
     void *ntt_tables = nullptr;
+    void *dist_tables = nullptr;   // per-rank tables of the distributed transform (ntt.cu)
+    void *comm = nullptr;          // communicator of the one-proof-across-N-GPUs mode (dist.cu): NCCL or in-process
+    int stream_priority = 0;
     // stage timers
     cudaEvent_t ev[zk::ST_COUNT][2];
     bool ev_used[zk::ST_COUNT];

@@ -97,9 +97,10 @@ int32_t zkpor_ctx_destroy(zkpor_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
     zk::DevBuf *bufs[] = {&ctx->in_points, &ctx->in_scalars, &ctx->sort_idx, &ctx->sort_idx2, &ctx->view_cnt, &ctx->view_order, &ctx->part_buf, &ctx->part_meta, &ctx->bucket_cnt, &ctx->bucket_off, &ctx->bucket_cur,
-                          &ctx->buckets, &ctx->partials, &ctx->windows, &ctx->misc, &ctx->ntt_a, &ctx->ntt_b, &ctx->ntt_c, &ctx->io, &ctx->heavy, &ctx->heavy_part, &ctx->order, &ctx->tree_a, &ctx->tree_b, &ctx->tree_meta};
+                          &ctx->buckets, &ctx->partials, &ctx->windows, &ctx->misc, &ctx->ntt_a, &ctx->ntt_b, &ctx->ntt_c, &ctx->io, &ctx->heavy, &ctx->heavy_part, &ctx->order, &ctx->tree_a, &ctx->tree_b, &ctx->tree_meta, &ctx->dist_tmp};
     for (auto *b : bufs) b->release();
     zk_free_poseidon(ctx); zk_free_ntt(ctx);
+    zk::comm_free(ctx);
     for (auto &r : ctx->klog) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -12,6 +12,7 @@
 // A, B1, B2 and K multiply (subsets of) the SAME wire vector, so the digits and the counting sort by bucket are computed
 // once over all wires; each multiplication then takes its own view of the shared lists (msm_view: skip bitmap + rank map).
 #include "internal.h"
+#include <algorithm>
 #include <cstdlib>
 
 using namespace ff;
@@ -76,9 +77,12 @@ static void assemble_proof(const ProofParts &pp, const G1Affine &alpha1, const G
     *out_len = len;
 }
 
+static int32_t combine_commit(zkpor_ctx *ctx, zkpor_pk *pk, G1XYZZ *commit, G1XYZZ *pok);
+
 int32_t pk_commit_and_pok(zkpor_ctx *ctx, zkpor_pk *pk, const Fr *d_wires, G1XYZZ *commit, G1XYZZ *pok) {
     *commit = G1XYZZ::inf(); *pok = G1XYZZ::inf();
-    if (!pk->has_commitment || pk->n_ck == 0) return ZKPOR_OK;
+    if (!pk->has_commitment) return ZKPOR_OK;
+    if (pk->n_ck == 0) return combine_commit(ctx, pk, commit, pok);
     ZK_TRY(pk->sub.reserve(pk->n_ck * 32));
     Fr *sub = pk->sub.as<Fr>();
     MsmSorted srt;
@@ -86,6 +90,16 @@ int32_t pk_commit_and_pok(zkpor_ctx *ctx, zkpor_pk *pk, const Fr *d_wires, G1XYZ
     ZK_TRY(msm_sort(ctx, sub, pk->n_ck, ZKPOR_SCALARS_MONT, &srt));
     ZK_TRY(msm_accumulate_g1(ctx, pk->ck, srt, commit));
     ZK_TRY(msm_accumulate_g1(ctx, pk->ck_sigma, srt, pok));
+    return combine_commit(ctx, pk, commit, pok);
+}
+
+// sharded key: every rank has summed its share of the committed wires; all ranks need the whole commitment (the challenge wire)
+static int32_t combine_commit(zkpor_ctx *ctx, zkpor_pk *pk, G1XYZZ *commit, G1XYZZ *pok) {
+    if (pk->shard_world <= 1) return ZKPOR_OK;
+    G1XYZZ mine[2] = {*commit, *pok}, all[2 * 8];
+    ZK_TRY(comm_all_gather_host(ctx, mine, all, sizeof mine));
+    *commit = G1XYZZ::inf(); *pok = G1XYZZ::inf();
+    for (int j = 0; j < pk->shard_world; j++) { commit->add(all[2 * j]); pok->add(all[2 * j + 1]); }
     return ZKPOR_OK;
 }
 
@@ -105,45 +119,51 @@ int32_t zkpor_pk_free(zkpor_ctx *ctx, zkpor_pk *pk) {
     return ZKPOR_OK;
 }
 
-int32_t zkpor_pk_upload(zkpor_ctx *ctx, const zkpor_pk_desc *d, zkpor_pk **out) {
+// Uploads the part of the key that multiplies wires [w0, w1) (w0 a multiple of 32), the committed wires number [c0, c1) and
+// Z[z0, z1); the whole key is the range (0, n_wires, 0, n_committed, 0, n_z).  `d` always describes the WHOLE key.
+static int32_t pk_upload_range(zkpor_ctx *ctx, const zkpor_pk_desc *d, uint64_t w0, uint64_t w1, uint64_t c0, uint64_t c1, uint64_t z0, uint64_t z1,
+                               int rank, int world, zkpor_pk **out) {
     ZK_REQUIRE(ctx && d && out, "pk_upload: null argument");
     ZK_REQUIRE(d->log_n >= 1 && d->log_n <= 28, "pk_upload: log_n out of range");
     ZK_REQUIRE(d->g1_alpha && d->g1_beta && d->g1_delta && d->g2_beta && d->g2_delta, "pk_upload: missing alpha/beta/delta");
     ZK_REQUIRE(d->n_wires < (1ull << 32), "pk_upload: too many wires");
     ZK_REQUIRE(d->n_committed == 0 || (d->ck_basis && d->ck_basis_exp_sigma && (d->n_wires == 0 || d->private_committed)),
                "pk_upload: n_committed > 0 needs ck_basis, ck_basis_exp_sigma and (with wire maps) private_committed");
+    ZK_REQUIRE(world == 1 || d->n_wires > 0, "pk_upload_shard: the key needs its infinity maps");
     ZK_CUDA(cudaSetDevice(ctx->device));
     zkpor_pk *pk = new zkpor_pk();
     *out = nullptr;
-    pk->log_n = d->log_n; pk->n_wires = d->n_wires;
-    pk->n_a = d->n_a; pk->n_b = d->n_b; pk->n_k = d->n_k; pk->n_z = d->n_z; pk->n_ck = d->n_committed;
+    pk->log_n = d->log_n; pk->n_wires = w1 - w0; pk->n_wires_total = d->n_wires; pk->wire_first = w0; pk->z_first = z0;
+    pk->shard_rank = rank; pk->shard_world = world;
+    pk->n_z = z1 - z0; pk->n_ck = c1 - c0;
     pk->has_commitment = d->n_committed > 0 || d->ck_basis != nullptr;
     memcpy(&pk->alpha1, d->g1_alpha, 64); memcpy(&pk->beta1, d->g1_beta, 64); memcpy(&pk->delta1, d->g1_delta, 64);
     memcpy(&pk->beta2, d->g2_beta, 128); memcpy(&pk->delta2, d->g2_delta, 128);
     int32_t rc = ZKPOR_OK;
-    auto up = [&](void **dst, const void *src, size_t bytes) { if (rc == ZKPOR_OK) rc = upload(dst, src, bytes); };
-    up((void **)&pk->A, d->g1_a, d->n_a * 64); up((void **)&pk->B1, d->g1_b, d->n_b * 64); up((void **)&pk->K, d->g1_k, d->n_k * 64);
-    up((void **)&pk->Z, d->g1_z, d->n_z * 64); up((void **)&pk->B2, d->g2_b, d->n_b * 128);
-    up((void **)&pk->ck, d->ck_basis, d->n_committed * 64); up((void **)&pk->ck_sigma, d->ck_basis_exp_sigma, d->n_committed * 64);
-    if (rc == ZKPOR_OK && d->n_wires > 0) {
+    auto up = [&](void **dst, const void *src, size_t first, size_t count, size_t elem) {
+        if (rc == ZKPOR_OK) rc = upload(dst, (const uint8_t *)src + first * elem, count * elem);
+    };
+    uint64_t ra0 = 0, rb0 = 0, rk0 = 0, ra1 = d->n_a, rb1 = d->n_b, rk1 = d->n_k;   // this range's slice of the compact arrays
+    if (d->n_wires > 0) {
         if (!d->infinity_a || !d->infinity_b) { set_error("pk_upload: infinity maps missing"); rc = ZKPOR_ERR_INVALID_ARG; }
         else {
             std::vector<uint32_t> ic;
             std::vector<uint8_t> drop(d->n_wires, 0);
             for (uint64_t i = 0; i < d->n_committed; i++) {
                 if (d->private_committed[i] >= d->n_wires) { set_error("pk_upload: committed wire out of range"); rc = ZKPOR_ERR_INVALID_ARG; break; }
-                drop[d->private_committed[i]] = 1; ic.push_back((uint32_t)d->private_committed[i]);
+                drop[d->private_committed[i]] = 1;
+                if (i >= c0 && i < c1) ic.push_back((uint32_t)d->private_committed[i]);
             }
             if (rc == ZKPOR_OK && pk->has_commitment) {
                 if (d->commitment_index >= d->n_wires) { set_error("pk_upload: commitment wire out of range"); rc = ZKPOR_ERR_INVALID_ARG; }
                 else drop[d->commitment_index] = 1;
             }
             if (rc == ZKPOR_OK) {
-                // per 32 wires: skip bits and the rank (index in the compact key array) of the first wire of the word
-                const uint64_t words = (d->n_wires + 31) / 32;
+                // per 32 wires: skip bits and the rank (index in this range's compact key array) of the first wire of the word
+                const uint64_t words_all = (d->n_wires + 31) / 32, word0 = w0 / 32, words = (w1 - w0 + 31) / 32;
                 std::vector<uint2> ma(words), mb(words), mk(words);
-                uint32_t ra = 0, rb = 0, rk = 0;
-                for (uint64_t w = 0; w < words; w++) {
+                uint64_t ra = 0, rb = 0, rk = 0;
+                for (uint64_t w = 0; w < words_all; w++) {
                     uint32_t ba = 0, bb = 0, bk = 0;
                     for (uint32_t j = 0; j < 32; j++) {
                         const uint64_t i = w * 32 + j;
@@ -152,23 +172,59 @@ int32_t zkpor_pk_upload(zkpor_ctx *ctx, const zkpor_pk_desc *d, zkpor_pk **out) 
                         if (!in || d->infinity_b[i]) bb |= 1u << j;
                         if (!in || i < d->n_public || drop[i]) bk |= 1u << j;
                     }
-                    ma[w] = make_uint2(ba, ra); mb[w] = make_uint2(bb, rb); mk[w] = make_uint2(bk, rk);
+                    if (w == word0) { ra0 = ra; rb0 = rb; rk0 = rk; }
+                    if (w == word0 + words) { ra1 = ra; rb1 = rb; rk1 = rk; }
+                    if (w >= word0 && w < word0 + words) {
+                        const uint64_t k = w - word0;
+                        ma[k] = make_uint2(ba, (uint32_t)(ra - ra0)); mb[k] = make_uint2(bb, (uint32_t)(rb - rb0)); mk[k] = make_uint2(bk, (uint32_t)(rk - rk0));
+                    }
                     ra += 32 - __builtin_popcount(ba); rb += 32 - __builtin_popcount(bb); rk += 32 - __builtin_popcount(bk);
                 }
+                if (word0 >= words_all) { ra0 = ra; rb0 = rb; rk0 = rk; }
+                if (word0 + words >= words_all) { ra1 = ra; rb1 = rb; rk1 = rk; }
                 if (ra != d->n_a || rb != d->n_b || rk != d->n_k) {
-                    set_error("pk_upload: key sizes inconsistent with infinity/commitment maps (A %u/%llu, B %u/%llu, K %u/%llu)", ra,
-                              (unsigned long long)d->n_a, rb, (unsigned long long)d->n_b, rk, (unsigned long long)d->n_k);
+                    set_error("pk_upload: key sizes inconsistent with infinity/commitment maps (A %llu/%llu, B %llu/%llu, K %llu/%llu)", (unsigned long long)ra,
+                              (unsigned long long)d->n_a, (unsigned long long)rb, (unsigned long long)d->n_b, (unsigned long long)rk, (unsigned long long)d->n_k);
                     rc = ZKPOR_ERR_INVALID_ARG;
                 }
-                up((void **)&pk->map_a, ma.data(), words * sizeof(uint2)); up((void **)&pk->map_b, mb.data(), words * sizeof(uint2));
-                up((void **)&pk->map_k, mk.data(), words * sizeof(uint2));
+                up((void **)&pk->map_a, ma.data(), 0, words, sizeof(uint2)); up((void **)&pk->map_b, mb.data(), 0, words, sizeof(uint2));
+                up((void **)&pk->map_k, mk.data(), 0, words, sizeof(uint2));
             }
-            up((void **)&pk->idx_c, ic.data(), ic.size() * 4);
+            up((void **)&pk->idx_c, ic.data(), 0, ic.size(), 4);
         }
     }
+    pk->n_a = ra1 - ra0; pk->n_b = rb1 - rb0; pk->n_k = rk1 - rk0;
+    up((void **)&pk->A, d->g1_a, ra0, pk->n_a, 64); up((void **)&pk->B1, d->g1_b, rb0, pk->n_b, 64); up((void **)&pk->K, d->g1_k, rk0, pk->n_k, 64);
+    up((void **)&pk->Z, d->g1_z, z0, pk->n_z, 64); up((void **)&pk->B2, d->g2_b, rb0, pk->n_b, 128);
+    up((void **)&pk->ck, d->ck_basis, c0, pk->n_ck, 64); up((void **)&pk->ck_sigma, d->ck_basis_exp_sigma, c0, pk->n_ck, 64);
     if (rc == ZKPOR_OK && d->n_z != (1ull << d->log_n) - 1 && d->n_wires > 0) { set_error("pk_upload: len(Z) must be 2^log_n - 1"); rc = ZKPOR_ERR_INVALID_ARG; }
     if (rc != ZKPOR_OK) { zkpor_pk_free(ctx, pk); return rc; }
     *out = pk;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_pk_upload(zkpor_ctx *ctx, const zkpor_pk_desc *d, zkpor_pk **out) {
+    ZK_REQUIRE(ctx && d && out, "pk_upload: null argument");
+    return pk_upload_range(ctx, d, 0, d->n_wires, 0, d->n_committed, 0, d->n_z, 0, 1, out);
+}
+
+// point-chunk split of the key over the ranks of the context's group: wires in `world` contiguous ranges (multiples of 32), the committed
+// wires by count, Z in the n/world chunks that computeH's sharded transform leaves on each rank
+int32_t zkpor_pk_upload_shard(zkpor_ctx *ctx, const zkpor_pk_desc *d, zkpor_pk **out) {
+    ZK_REQUIRE(ctx && d && out, "pk_upload_shard: null argument");
+    int rank, world; comm_info(ctx, &rank, &world);
+    ZK_REQUIRE(d->log_n >= 1 && d->log_n <= 28 && ((uint64_t)1 << d->log_n) >= (uint64_t)world * world * 2, "pk_upload_shard: domain too small for this many ranks");
+    const uint64_t W = d->n_wires, per = (((W + world - 1) / world) + 31) & ~31ull;
+    const uint64_t w0 = std::min(W, per * rank), w1 = std::min(W, w0 + per);
+    const uint64_t c0 = d->n_committed * rank / world, c1 = d->n_committed * (rank + 1) / world;
+    const uint64_t m = ((uint64_t)1 << d->log_n) / world, z0 = std::min(d->n_z, m * rank), z1 = std::min(d->n_z, m * (rank + 1));
+    return pk_upload_range(ctx, d, w0, w1, c0, c1, z0, z1, rank, world, out);
+}
+
+int32_t zkpor_pk_shard_info(zkpor_pk *pk, uint64_t out8[8]) {
+    ZK_REQUIRE(pk && out8, "pk_shard_info: null argument");
+    out8[0] = pk->shard_rank; out8[1] = pk->shard_world; out8[2] = pk->wire_first; out8[3] = pk->n_wires; out8[4] = pk->n_a; out8[5] = pk->n_b;
+    out8[6] = pk->n_k; out8[7] = pk->n_z;
     return ZKPOR_OK;
 }
 
@@ -187,10 +243,13 @@ int32_t zkpor_pk_commit(zkpor_ctx *ctx, zkpor_pk *pk, const void *committed_valu
 
 // shared body of zkpor_groth16_prove (a, b, c from the caller) and zkpor_groth16_prove_wires (a, b, c = L w, R w, O w on the device)
 // and zkpor_groth16_prove_solve (the wires themselves come from the device solver: `prog` set, `wires` = the circuit's inputs)
-static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_program *prog, const void *wires, const void *a, const void *b,
+static int32_t prove_body(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_program *prog, const void *wires, const void *a, const void *b,
                           const void *c, uint64_t n_constraints, const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
-    ZK_REQUIRE(pk->n_wires > 0, "prove: key was uploaded without wire maps (sharded key?)");
-    const size_t n = (size_t)1 << pk->log_n;
+    ZK_REQUIRE(pk->n_wires_total > 0, "prove: key was uploaded without wire maps (a key for zkpor_groth16_prove_partial?)");
+    int rank, world; comm_info(ctx, &rank, &world);
+    ZK_REQUIRE(pk->shard_world == world && pk->shard_rank == rank, "prove: the key's shard does not match the context's rank in its group");
+    ZK_REQUIRE(world == 1 || cs != nullptr, "prove: one proof across several GPUs needs the constraint system on the device (prove_wires / prove_solve)");
+    const size_t n = (size_t)1 << pk->log_n, m = n / (size_t)world;   // m: this rank's share of the domain
     ZK_REQUIRE(n_constraints > 0 && n_constraints <= n, "prove: n_constraints exceeds the domain");
     ZK_CUDA(cudaSetDevice(ctx->device));
     stages_reset(ctx);
@@ -202,8 +261,9 @@ static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_pr
     bool commit_done = false;
     if (prog != nullptr) {
         // r1cs.Solve on the device: inputs -> wires[1 ..], every other wire by the level schedule; the commitment hint leaves the
-        // commitment and its proof of knowledge behind
-        ZK_TRY(pk->wires.reserve(pk->n_wires * 32));
+        // commitment and its proof of knowledge behind.  Sharded: every rank solves the whole system (the schedule is a latency
+        // chain, not throughput work) and contributes its share of the commitment.
+        ZK_TRY(pk->wires.reserve(pk->n_wires_total * 32));
         Fr *w = pk->wires.as<Fr>();
         const Fr one = Fr::one();
         stage_begin(ctx, ST_H2D);
@@ -215,15 +275,26 @@ static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_pr
         dw = w;
     } else {
         stage_begin(ctx, ST_H2D);
-        ZK_TRY(to_device(ctx, wires, pk->n_wires * 32, pk->wires, &dw));
+        ZK_TRY(to_device(ctx, wires, pk->n_wires_total * 32, pk->wires, &dw));
         stage_end(ctx, ST_H2D);
     }
-    const size_t bytes = n * sizeof(Fr), in_bytes = n_constraints * sizeof(Fr);
+    const size_t bytes = m * sizeof(Fr), in_bytes = n_constraints * sizeof(Fr);
     ZK_TRY(ctx->ntt_a.reserve(bytes)); ZK_TRY(ctx->ntt_b.reserve(bytes)); ZK_TRY(ctx->ntt_c.reserve(bytes));
     const void *src[3] = {a, b, c};
     Fr *dst[3] = {ctx->ntt_a.as<Fr>(), ctx->ntt_b.as<Fr>(), ctx->ntt_c.as<Fr>()};
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));   // the previous call's use of the NTT buffers is over
-    if (cs != nullptr) {
+    if (world > 1) {
+        // this rank's rows rank, rank + world, ... of a, b, c: the cyclic split the sharded transform starts from
+        ZK_TRY(ctx->dist_tmp.reserve(bytes));
+        ZK_TRY(r1cs_eval_strided_dev(ctx, cs, (const Fr *)dw, dst[0], dst[1], dst[2], (uint64_t)rank, (uint64_t)world, m));
+        int32_t ok_all[8], ok_mine = prog != nullptr ? r1cs_check_dev(ctx, dst[0], dst[1], dst[2], m) : ZKPOR_OK;
+        if (prog != nullptr) {
+            ZK_TRY(comm_all_gather_host(ctx, &ok_mine, ok_all, sizeof ok_mine));
+            for (int j = 0; j < world; j++)
+                if (ok_all[j] != ZKPOR_OK) { if (ok_mine == ZKPOR_OK) set_error("solve: a constraint is not satisfied (found by rank %d)", j); return ok_all[j]; }
+            stage_end(ctx, ST_SOLVE);
+        }
+    } else if (cs != nullptr) {
         // constraint evaluation on the device: needs only the wires, runs ahead of the multiplications on the compute stream
         for (int k = 0; k < 3; k++) if (bytes > in_bytes) ZK_CUDA(cudaMemsetAsync((uint8_t *)dst[k] + in_bytes, 0, bytes - in_bytes, ctx->stream));
         ZK_TRY(r1cs_eval_dev(ctx, cs, (const Fr *)dw, dst[0], dst[1], dst[2]));
@@ -240,7 +311,8 @@ static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_pr
     // computeH runs on the copy stream, right behind the transfers of a, b, c, concurrently with the wire-side sorts and
     // multiplications of the compute stream: the counting sorts are bound by L2 atomics and scattered stores and leave the
     // integer pipe idle, which the NTT butterflies fill.  The Z multiplication waits for h (copy_done).
-    if (overlap_ntt()) {
+    const bool overlap = overlap_ntt() && world == 1;
+    if (overlap) {
         if (cs != nullptr) {   // a, b, c were produced on the compute stream
             ZK_CUDA(cudaEventRecord(ctx->copy_done, ctx->stream));
             ZK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done, 0));
@@ -256,28 +328,47 @@ static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_pr
     MsmSorted srt;
     if (!commit_done) ZK_TRY(pk_commit_and_pok(ctx, pk, (const Fr *)dw, &pp.commit, &pp.pok));
     pp.ar = G1XYZZ::inf(); pp.bs1 = G1XYZZ::inf(); pp.bs2 = G2XYZZ::inf(); pp.krs_k = G1XYZZ::inf(); pp.krs_z = G1XYZZ::inf();
-    // one digit extraction + counting sort over the whole wire vector, four accumulations through their wire maps
-    ZK_TRY(msm_sort(ctx, dw, pk->n_wires, ZKPOR_SCALARS_MONT, &srt));
-    MsmSorted view;
-    if (pk->n_a) {
-        ZK_TRY(msm_view(ctx, srt, pk->map_a, &view));
-        ZK_TRY(msm_accumulate_g1(ctx, pk->A, view, &pp.ar, pk->n_a));
-    }
-    if (pk->n_b) {
-        ZK_TRY(msm_view(ctx, srt, pk->map_b, &view));      // one view, two accumulations (G1 and G2)
-        ZK_TRY(msm_accumulate_g1(ctx, pk->B1, view, &pp.bs1, pk->n_b));
-        ZK_TRY(msm_accumulate_g2(ctx, pk->B2, view, &pp.bs2, pk->n_b));
-    }
-    if (pk->n_k) {
-        ZK_TRY(msm_view(ctx, srt, pk->map_k, &view));
-        ZK_TRY(msm_accumulate_g1(ctx, pk->K, view, &pp.krs_k, pk->n_k));
+    // one digit extraction + counting sort over (this rank's range of) the wire vector, four accumulations through their wire maps
+    const Fr *dw_mine = (const Fr *)dw + pk->wire_first;
+    if (pk->n_wires) {
+        ZK_TRY(msm_sort(ctx, dw_mine, pk->n_wires, ZKPOR_SCALARS_MONT, &srt));
+        MsmSorted view;
+        if (pk->n_a) {
+            ZK_TRY(msm_view(ctx, srt, pk->map_a, &view));
+            ZK_TRY(msm_accumulate_g1(ctx, pk->A, view, &pp.ar, pk->n_a));
+        }
+        if (pk->n_b) {
+            ZK_TRY(msm_view(ctx, srt, pk->map_b, &view));      // one view, two accumulations (G1 and G2)
+            ZK_TRY(msm_accumulate_g1(ctx, pk->B1, view, &pp.bs1, pk->n_b));
+            ZK_TRY(msm_accumulate_g2(ctx, pk->B2, view, &pp.bs2, pk->n_b));
+        }
+        if (pk->n_k) {
+            ZK_TRY(msm_view(ctx, srt, pk->map_k, &view));
+            ZK_TRY(msm_accumulate_g1(ctx, pk->K, view, &pp.krs_k, pk->n_k));
+        }
     }
     ZK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
-    if (!overlap_ntt()) ZK_TRY(compute_h_dev(ctx, dst[0], dst[1], dst[2], pk->log_n));
-    ZK_TRY(msm_g1_dev(ctx, pk->Z, dst[0], pk->n_z, ZKPOR_SCALARS_MONT, &pp.krs_z));
+    if (world > 1) ZK_TRY(compute_h_dist(ctx, dst[0], dst[1], dst[2], ctx->dist_tmp.as<Fr>(), pk->log_n));
+    else if (!overlap) ZK_TRY(compute_h_dev(ctx, dst[0], dst[1], dst[2], pk->log_n));
+    if (pk->n_z) ZK_TRY(msm_g1_dev(ctx, pk->Z, dst[0], pk->n_z, ZKPOR_SCALARS_MONT, &pp.krs_z));
+    if (world > 1) {
+        // the one collective of the multiplications: 4 G1 + 1 G2 partial sums per rank, every rank finishes the proof
+        struct Part { G1XYZZ ar, bs1, krs_k, krs_z; G2XYZZ bs2; } mine = {pp.ar, pp.bs1, pp.krs_k, pp.krs_z, pp.bs2}, all[8];
+        ZK_TRY(comm_all_gather_host(ctx, &mine, all, sizeof mine));
+        pp.ar = G1XYZZ::inf(); pp.bs1 = G1XYZZ::inf(); pp.bs2 = G2XYZZ::inf(); pp.krs_k = G1XYZZ::inf(); pp.krs_z = G1XYZZ::inf();
+        for (int j = 0; j < world; j++) { pp.ar.add(all[j].ar); pp.bs1.add(all[j].bs1); pp.krs_k.add(all[j].krs_k); pp.krs_z.add(all[j].krs_z); pp.bs2.add(all[j].bs2); }
+    }
     assemble_proof(pp, pk->alpha1, pk->beta1, pk->delta1, pk->beta2, pk->delta2, r_be, s_be, pk->has_commitment, out_proof, out_len);
     stages_collect(ctx);
     return ZKPOR_OK;
+}
+
+// a failing rank of a sharded proof must not leave its peers waiting at a host barrier
+static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_program *prog, const void *wires, const void *a, const void *b,
+                          const void *c, uint64_t n_constraints, const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
+    const int32_t rc = prove_body(ctx, pk, cs, prog, wires, a, b, c, n_constraints, r_be, s_be, out_proof, out_len);
+    if (rc != ZKPOR_OK) comm_abort(ctx);
+    return rc;
 }
 
 int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, const void *a, const void *b, const void *c,
@@ -289,7 +380,7 @@ int32_t zkpor_groth16_prove(zkpor_ctx *ctx, zkpor_pk *pk, const void *wires, con
 int32_t zkpor_groth16_prove_wires(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, const void *wires, const uint8_t r_be[32], const uint8_t s_be[32],
                                   uint8_t *out_proof, uint32_t *out_len) {
     ZK_REQUIRE(ctx && pk && cs && wires && r_be && s_be && out_proof && out_len, "prove_wires: null argument");
-    ZK_REQUIRE(r1cs_wires(cs) == pk->n_wires, "prove_wires: the constraint system and the key disagree on the number of wires");
+    ZK_REQUIRE(r1cs_wires(cs) == pk->n_wires_total, "prove_wires: the constraint system and the key disagree on the number of wires");
     return prove_impl(ctx, pk, cs, nullptr, wires, nullptr, nullptr, nullptr, r1cs_rows(cs), r_be, s_be, out_proof, out_len);
 }
 
@@ -297,7 +388,7 @@ int32_t zkpor_groth16_prove_solve(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_program *p
                                   const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
     ZK_REQUIRE(ctx && pk && prog && inputs && r_be && s_be && out_proof && out_len, "prove_solve: null argument");
     zkpor_r1cs *cs = program_matrices(prog);
-    ZK_REQUIRE(r1cs_wires(cs) == pk->n_wires, "prove_solve: the program and the key disagree on the number of wires");
+    ZK_REQUIRE(r1cs_wires(cs) == pk->n_wires_total, "prove_solve: the program and the key disagree on the number of wires");
     return prove_impl(ctx, pk, cs, prog, inputs, nullptr, nullptr, nullptr, r1cs_rows(cs), r_be, s_be, out_proof, out_len);
 }
 

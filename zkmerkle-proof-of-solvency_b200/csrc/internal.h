@@ -25,6 +25,10 @@ struct zkpor_pk {
     ec::G1Affine alpha1, beta1, delta1;
     ec::G2Affine beta2, delta2;
     bool has_commitment = false;
+    // one proof across N GPUs (zkpor_pk_upload_shard): this key holds the points of wires [wire_first, wire_first + n_wires) out of
+    // n_wires_total, Z[z_first, z_first + n_z) and the commitment basis of its share of the committed wires
+    int shard_rank = 0, shard_world = 1;
+    uint64_t wire_first = 0, n_wires_total = 0, z_first = 0;
     zk::DevBuf wires, sub;
 };
 
@@ -92,6 +96,20 @@ int32_t r1cs_check_dev(zkpor_ctx *ctx, const ff::Fr *d_a, const ff::Fr *d_b, con
 // NTT (device-resident data)
 int32_t ntt_dev(zkpor_ctx *ctx, ff::Fr *d_data, uint32_t log_n, bool inverse, bool dit, bool coset);
 int32_t compute_h_dev(zkpor_ctx *ctx, ff::Fr *d_a, ff::Fr *d_b, ff::Fr *d_c, uint32_t log_n);   // result in d_a (bit-reversed)
+
+// communicator of the sharded mode (dist.cu).  all_to_all: chunk i of `send` goes to rank i, chunk j of `recv` comes from rank j
+// (device buffers, bytes per peer); all_gather_host: `bytes` of host data from every rank, in rank order, to every rank.
+void comm_info(zkpor_ctx *ctx, int *rank, int *world);
+int32_t comm_all_to_all(zkpor_ctx *ctx, const void *send, void *recv, size_t bytes_per_peer);
+int32_t comm_all_gather_host(zkpor_ctx *ctx, const void *send, void *recv, size_t bytes);
+void comm_abort(zkpor_ctx *ctx);   // a failing rank releases its peers' host barriers (in-process group)
+void comm_free(zkpor_ctx *ctx);
+// computeH across the communicator's ranks (ntt.cu): a, b, c = this rank's n/N evaluations in cyclic order (row g + N j at j); result in
+// a = this rank's contiguous chunk of h in gnark's bit-reversed coefficient order; tmp = n/N elements of scratch
+int32_t compute_h_dist(zkpor_ctx *ctx, ff::Fr *a, ff::Fr *b, ff::Fr *c, ff::Fr *tmp, uint32_t log_n);
+// rows g, g + N, g + 2N, ... of a = L w, b = R w, c = O w (j-th output = row offset + j*stride; rows beyond the system are zero)
+int32_t r1cs_eval_strided_dev(zkpor_ctx *ctx, zkpor_r1cs *cs, const ff::Fr *d_wires, ff::Fr *d_a, ff::Fr *d_b, ff::Fr *d_c, uint64_t offset,
+                              uint64_t stride, uint64_t count);
 
 // host helpers
 void fe_from_be32(ff::Fr *out_plain, const uint8_t be[32]);    // canonical big-endian -> plain limbs (not Montgomery)

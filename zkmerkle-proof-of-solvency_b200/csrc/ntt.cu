@@ -251,6 +251,141 @@ int32_t compute_h_dev(zkpor_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n) {
     return ZKPOR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ computeH across N GPUs
+// One size-n transform split over N = 2^k ranks with ONE all-to-all: rank g holds the cyclic subsequence
+// x_g[j] = x[g + N j] (m = n/N elements).
+//   inverse (evaluations -> coefficients):  X[k' + m t] = sum_g w^(-g(k' + m t)) Y_g[k'],  Y_g = the size-m inverse transform of x_g:
+//     local DIF (bit-reversed positions p, k' = bitrev(p)), scale by w^(-g k')/n, all-to-all (rank r takes positions [r m/N, (r+1) m/N)
+//     of every g), then a radix-N butterfly over g.  Rank r ends up with X[k' + m t] for its positions and every t, stored at
+//     [q N + bitrev_k(t)]: with that order the ranks' pieces are exactly the contiguous chunks [r m, (r+1) m) of the bit-reversed
+//     coefficient vector -- the order gnark stores pk.G1.Z in, so the Z multiplication shards by plain point chunks.
+//   forward (coefficients in that order -> evaluations, cyclic again): radix-N butterfly over t, all-to-all back, scale by w^(g k'),
+//     local DIT.
+// computeH = inverse, coset scale 5^k, forward (for a, b, c), a*b - c, inverse, scale 5^(-k) den: three exchange phases (3 + 3 + 1 vectors).
+struct DistDomain {
+    uint32_t log_n = 0, log_w = 0; int rank = -1;
+    Fr *inv_lo = nullptr, *inv_hi = nullptr;     // (w^-g)^e / n
+    Fr *invd_lo = nullptr, *invd_hi = nullptr;   // (w^-g)^e * den / n
+    Fr *fwd_lo = nullptr, *fwd_hi = nullptr;     // (w^g)^e
+    Fr *c5_lo = nullptr, *c5_hi = nullptr, *c5i_lo = nullptr, *c5i_hi = nullptr;   // 5^e, 5^-e for e < m
+    Fr *consts = nullptr;                        // om[g*N + t] = w^(m g t) (N*N), then om_inv (N*N), then 5^(m t), 5^(-m t) (N each)
+};
+struct DistCache { std::map<uint64_t, DistDomain> doms; };
+
+// in[g*chunk + q] (one value per source rank g) -> out[q*N + bitrev_k(t)] = (sum_g in[g][q] * om_inv[g][t]) * c(k') * cm[t],
+// k' = bitrev(first + q): the radix-N butterfly that completes an inverse transform, with the coset factor 5^(+-(k' + m t)) folded in
+__global__ void k_dist_bfly_inv(const Fr *__restrict__ in, Fr *__restrict__ out, const Fr *__restrict__ om_inv, const Fr *__restrict__ cm,
+                                const Fr *__restrict__ c_lo, const Fr *__restrict__ c_hi, uint32_t log_m, uint32_t log_w, size_t first, size_t chunk) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= chunk) return;
+    const uint32_t N = 1u << log_w;
+    const uint32_t kp = log_m ? (__brev((uint32_t)(first + q)) >> (32 - log_m)) : 0;
+    const Fr base = Fr::mul(ldg_fr(c_lo + (kp & ((1u << LO_BITS) - 1))), ldg_fr(c_hi + (kp >> LO_BITS)));
+    Fr x[8];
+    for (uint32_t g = 0; g < N; g++) x[g] = ld_fr(in + (size_t)g * chunk + q);
+    for (uint32_t t = 0; t < N; t++) {
+        Fr acc = x[0];
+        for (uint32_t g = 1; g < N; g++) acc = Fr::add(acc, Fr::mul(x[g], ldg_fr(om_inv + g * N + t)));
+        const uint32_t tr = log_w ? (__brev(t) >> (32 - log_w)) : 0;
+        st_fr(out + q * N + tr, Fr::mul(acc, Fr::mul(base, ldg_fr(cm + t))));
+    }
+}
+// in[q*N + bitrev_k(t)] -> out[g*chunk + q] = sum_t in[q][t] * om[g][t]: the radix-N butterfly that opens a forward transform
+__global__ void k_dist_bfly_fwd(const Fr *__restrict__ in, Fr *__restrict__ out, const Fr *__restrict__ om, uint32_t log_w, size_t chunk) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= chunk) return;
+    const uint32_t N = 1u << log_w;
+    Fr x[8];
+    for (uint32_t t = 0; t < N; t++) { const uint32_t tr = log_w ? (__brev(t) >> (32 - log_w)) : 0; x[t] = ld_fr(in + q * N + tr); }
+    for (uint32_t g = 0; g < N; g++) {
+        Fr acc = x[0];
+        for (uint32_t t = 1; t < N; t++) acc = Fr::add(acc, Fr::mul(x[t], ldg_fr(om + g * N + t)));
+        st_fr(out + (size_t)g * chunk + q, acc);
+    }
+}
+
+static int32_t get_dist_domain(zkpor_ctx *ctx, uint32_t log_n, uint32_t log_w, int rank, DistDomain **out) {
+    if (!ctx->dist_tables) ctx->dist_tables = new DistCache();
+    DistCache *cache = (DistCache *)ctx->dist_tables;
+    const uint64_t key = ((uint64_t)log_n << 32) | ((uint64_t)log_w << 16) | (uint64_t)rank;
+    auto it = cache->doms.find(key);
+    if (it != cache->doms.end()) { *out = &it->second; return ZKPOR_OK; }
+    DistDomain d; d.log_n = log_n; d.log_w = log_w; d.rank = rank;
+    const uint32_t log_m = log_n - log_w, N = 1u << log_w;
+    Fr root; memcpy(root.l, ROOT_2_28_PLAIN, 32); root = Fr::to_mont(root);
+    for (uint32_t i = log_n; i < 28; i++) root = Fr::sqr(root);
+    const Fr w = root, w_inv = Fr::inv(root);
+    const Fr five = Fr::from_u64(5), five_inv = Fr::inv(five);
+    const Fr n_inv = Fr::inv(Fr::from_u64(1ull << log_n));
+    Fr den = five; for (uint32_t i = 0; i < log_n; i++) den = Fr::sqr(den);
+    den = Fr::inv(Fr::sub(den, Fr::one()));
+    ZK_TRY(build_two_level(ctx, host_pow_u64(w_inv, (uint64_t)rank), n_inv, log_m, &d.inv_lo, &d.inv_hi));
+    ZK_TRY(build_two_level(ctx, host_pow_u64(w_inv, (uint64_t)rank), Fr::mul(n_inv, den), log_m, &d.invd_lo, &d.invd_hi));
+    ZK_TRY(build_two_level(ctx, host_pow_u64(w, (uint64_t)rank), Fr::one(), log_m, &d.fwd_lo, &d.fwd_hi));
+    ZK_TRY(build_two_level(ctx, five, Fr::one(), log_m, &d.c5_lo, &d.c5_hi));
+    ZK_TRY(build_two_level(ctx, five_inv, Fr::one(), log_m, &d.c5i_lo, &d.c5i_hi));
+    std::vector<Fr> hc(2 * (size_t)N * N + 2 * N);
+    const Fr om = host_pow_u64(w, 1ull << log_m), om_inv = host_pow_u64(w_inv, 1ull << log_m);   // primitive N-th roots
+    const Fr c5m = host_pow_u64(five, 1ull << log_m), c5mi = host_pow_u64(five_inv, 1ull << log_m);
+    for (uint32_t g = 0; g < N; g++) for (uint32_t t = 0; t < N; t++) {
+        hc[(size_t)g * N + t] = host_pow_u64(om, (uint64_t)g * t);
+        hc[(size_t)N * N + (size_t)g * N + t] = host_pow_u64(om_inv, (uint64_t)g * t);
+    }
+    for (uint32_t t = 0; t < N; t++) { hc[2 * (size_t)N * N + t] = host_pow_u64(c5m, t); hc[2 * (size_t)N * N + N + t] = host_pow_u64(c5mi, t); }
+    ZK_CUDA(cudaMalloc((void **)&d.consts, hc.size() * sizeof(Fr)));
+    ZK_CUDA(cudaMemcpy(d.consts, hc.data(), hc.size() * sizeof(Fr), cudaMemcpyHostToDevice));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cache->doms[key] = d;
+    *out = &cache->doms[key];
+    return ZKPOR_OK;
+}
+
+// x: this rank's m elements in cyclic order; result: this rank's chunk of the bit-reversed coefficient vector, times 5^(+k) (coset > 0)
+// or 5^(-k) den (coset < 0).  tmp: m elements of scratch.
+static int32_t dist_inverse(zkpor_ctx *ctx, DistDomain *dd, NttDomain *loc, Fr *x, Fr *tmp, int coset) {
+    const uint32_t log_m = dd->log_n - dd->log_w, N = 1u << dd->log_w;
+    const size_t m = (size_t)1 << log_m, chunk = m >> dd->log_w;
+    ZK_TRY(run_dif(ctx, x, loc->tw_inv, log_m));
+    if (coset < 0) ZK_LAUNCH(ctx, k_scale_pow, grid_for(m, 256), 256, 0, x, dd->invd_lo, dd->invd_hi, log_m, 1);
+    else ZK_LAUNCH(ctx, k_scale_pow, grid_for(m, 256), 256, 0, x, dd->inv_lo, dd->inv_hi, log_m, 1);
+    ZK_TRY(comm_all_to_all(ctx, x, tmp, chunk * sizeof(Fr)));
+    const Fr *lo = coset > 0 ? dd->c5_lo : dd->c5i_lo, *hi = coset > 0 ? dd->c5_hi : dd->c5i_hi;
+    const Fr *om_inv = dd->consts + (size_t)N * N, *cm = dd->consts + 2 * (size_t)N * N + (coset > 0 ? 0 : N);
+    ZK_LAUNCH(ctx, k_dist_bfly_inv, grid_for(chunk, 128), 128, 0, (const Fr *)tmp, x, om_inv, cm, lo, hi, log_m, dd->log_w, (size_t)dd->rank * chunk, chunk);
+    return ZKPOR_OK;
+}
+
+// x: this rank's chunk of the bit-reversed coefficient vector; result: this rank's m evaluations in cyclic order
+static int32_t dist_forward(zkpor_ctx *ctx, DistDomain *dd, NttDomain *loc, Fr *x, Fr *tmp) {
+    const uint32_t log_m = dd->log_n - dd->log_w;
+    const size_t m = (size_t)1 << log_m, chunk = m >> dd->log_w;
+    ZK_LAUNCH(ctx, k_dist_bfly_fwd, grid_for(chunk, 128), 128, 0, (const Fr *)x, tmp, (const Fr *)dd->consts, dd->log_w, chunk);
+    ZK_TRY(comm_all_to_all(ctx, tmp, x, chunk * sizeof(Fr)));
+    ZK_LAUNCH(ctx, k_scale_pow, grid_for(m, 256), 256, 0, x, dd->fwd_lo, dd->fwd_hi, log_m, 1);
+    ZK_TRY(run_dit(ctx, x, loc->tw_fwd, log_m));
+    return ZKPOR_OK;
+}
+
+int32_t compute_h_dist(zkpor_ctx *ctx, Fr *a, Fr *b, Fr *c, Fr *tmp, uint32_t log_n) {
+    int rank = 0, world = 1;
+    comm_info(ctx, &rank, &world);
+    uint32_t log_w = 0;
+    while ((1 << log_w) < world) log_w++;
+    ZK_REQUIRE((1 << log_w) == world && log_w <= 3, "compute_h: the number of ranks must be 1, 2, 4 or 8");
+    ZK_REQUIRE(log_n >= 2 * log_w + 1 && log_n <= 28, "compute_h: domain too small for this many ranks");
+    DistDomain *dd; ZK_TRY(get_dist_domain(ctx, log_n, log_w, rank, &dd));
+    NttDomain *loc; ZK_TRY(get_domain(ctx, log_n - log_w, &loc));
+    const size_t m = (size_t)1 << (log_n - log_w);
+    stage_begin(ctx, ST_NTT);
+    Fr *v[3] = {a, b, c};
+    for (int k = 0; k < 3; k++) ZK_TRY(dist_inverse(ctx, dd, loc, v[k], tmp, +1));
+    for (int k = 0; k < 3; k++) ZK_TRY(dist_forward(ctx, dd, loc, v[k], tmp));
+    ZK_LAUNCH(ctx, k_ab_minus_c, grid_for(m, 256), 256, 0, a, (const Fr *)b, (const Fr *)c, m);
+    ZK_TRY(dist_inverse(ctx, dd, loc, a, tmp, -1));
+    stage_end(ctx, ST_NTT);
+    return ZKPOR_OK;
+}
+
 }  // namespace zk
 
 using namespace zk;
@@ -267,6 +402,16 @@ void zk_free_ntt(zkpor_ctx *ctx) {
     }
     delete cache;
     ctx->ntt_tables = nullptr;
+    if (ctx->dist_tables) {
+        DistCache *dc = (DistCache *)ctx->dist_tables;
+        for (auto &kv : dc->doms) {
+            DistDomain &d = kv.second;
+            Fr *ptrs[] = {d.inv_lo, d.inv_hi, d.invd_lo, d.invd_hi, d.fwd_lo, d.fwd_hi, d.c5_lo, d.c5_hi, d.c5i_lo, d.c5i_hi, d.consts};
+            for (Fr *p : ptrs) if (p) cudaFree(p);
+        }
+        delete dc;
+        ctx->dist_tables = nullptr;
+    }
 }
 
 int32_t zkpor_ntt(zkpor_ctx *ctx, void *data, uint32_t log_n, int32_t inverse, int32_t decimation, int32_t coset) {

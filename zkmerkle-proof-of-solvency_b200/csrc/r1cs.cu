@@ -24,6 +24,33 @@ __global__ void __launch_bounds__(256) k_r1cs_rows(const uint64_t *__restrict__ 
     out[row] = acc;
 }
 
+// j-th output = row offset + j*stride (the cyclic subsequence a rank of the distributed computeH holds); rows past the end are zero
+__global__ void __launch_bounds__(256) k_r1cs_rows_strided(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ wire_ids,
+                                                           const uint32_t *__restrict__ coeff_ids, const Fr *__restrict__ coeffs, uint32_t one_id,
+                                                           const Fr *__restrict__ w, uint64_t n_rows, uint64_t offset, uint64_t stride, uint64_t count,
+                                                           Fr *__restrict__ out) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const uint64_t row = offset + j * stride;
+    Fr acc = Fr::zero();
+    if (row < n_rows)
+        for (uint64_t e = row_ptr[row], end = row_ptr[row + 1]; e < end; e++) {
+            const uint32_t id = __ldg(coeff_ids + e);
+            const Fr v = w[__ldg(wire_ids + e)];
+            acc = Fr::add(acc, id == one_id ? v : Fr::mul(coeffs[id], v));
+        }
+    out[j] = acc;
+}
+
+int32_t r1cs_eval_strided_dev(zkpor_ctx *ctx, zkpor_r1cs *cs, const Fr *d_wires, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t offset, uint64_t stride,
+                              uint64_t count) {
+    Fr *outs[3] = {d_a, d_b, d_c};
+    for (int m = 0; m < 3; m++)
+        ZK_LAUNCH(ctx, k_r1cs_rows_strided, grid_for(count, 256), 256, 0, (const uint64_t *)cs->row_ptr[m], (const uint32_t *)cs->wire_ids[m],
+                  (const uint32_t *)cs->coeff_ids[m], (const Fr *)cs->coeffs, cs->one_id, d_wires, cs->n_rows, offset, stride, count, outs[m]);
+    return ZKPOR_OK;
+}
+
 int32_t r1cs_eval_dev(zkpor_ctx *ctx, zkpor_r1cs *cs, const Fr *d_wires, Fr *d_a, Fr *d_b, Fr *d_c) {
     Fr *outs[3] = {d_a, d_b, d_c};
     for (int m = 0; m < 3; m++)

@@ -19,21 +19,24 @@
 // The solver writes wire values only; a = Lw, b = Rw, c = Ow and the satisfaction check are one wide pass afterwards (r1cs.cu).
 #include "internal.h"
 #include <algorithm>
+#include <cstdlib>
 
 using namespace ff;
 using namespace ec;
 
 namespace zk {
 
-static const uint32_t NARROW_MAX = 96;          // levels up to this many instructions are fused into single-CTA runs
-static const int NARROW_THREADS = 1024;
+static const uint32_t NARROW_MAX = 96;          // levels up to this many instructions are fused into single-CTA runs (env ZKPOR_NARROW_MAX)
+static const int NARROW_THREADS = 1024;         // upper bound of the fused-run CTA (env ZKPOR_NARROW_THREADS picks fewer warps)
+static const uint64_t WIDE_G32_MAX = 1u << 15;  // wide levels up to this many instructions take a whole warp per instruction (env ZKPOR_WIDE_G32_MAX)
 static const uint64_t SOLVE_NONE = ~0ull;
 static const uint32_t HINT_BIT = 0x80000000u;
 
 enum StepKind { STEP_WIDE = 0, STEP_NARROW, STEP_COUNT, STEP_COMMIT };
-struct Step { int kind; uint64_t a, b; };       // WIDE: sched range [a, b); NARROW: levels [a, b); COUNT / COMMIT: hint id a
+struct Step { int kind; uint64_t a, b; bool has_div; };   // WIDE: sched range [a, b); NARROW: levels [a, b); COUNT / COMMIT: hint id a
 enum SolveErr { SE_OK = 0, SE_UNSOLVED = 1, SE_DIV0 = 2, SE_INDEX = 3, SE_HINT = 4 };
 
+struct Pending;
 struct ProgView {
     const uint64_t *ptr[3]; const uint32_t *wire[3], *coef[3];
     const uint64_t *aux_ptr; const uint32_t *aux_wire, *aux_coef;
@@ -43,7 +46,12 @@ struct ProgView {
     const uint64_t *table_ptr;
     uint64_t *solve_e;
     Fr *w; uint8_t *solved; unsigned long long *err;      // err: (code << 56) | row or hint id, first writer wins
+    struct Pending *pend;                                 // wide levels: divisions deferred to k_solve_div, slot = position in the level
+    uint8_t *step_div;                                    // dry run: step s has at least one division
 };
+// w[wire] = num / den, written by the evaluating group, consumed (and cleared) by k_solve_div
+struct alignas(16) Pending { Fr num, den; uint32_t wire, state, pad0, pad1; };   // state: 0 empty, 1 division, 2 division where den = 0 gives 0 (InvZero)
+static const uint64_t NO_SLOT = ~0ull;
 
 }  // namespace zk
 
@@ -55,6 +63,8 @@ struct zkpor_program {
     uint32_t *hint_fn = nullptr, *hint_param = nullptr, *hint_out = nullptr, *hint_nout = nullptr; uint64_t *hint_in0 = nullptr, *hint_in1 = nullptr;
     uint64_t *table_ptr = nullptr;
     uint64_t *solve_e = nullptr;
+    zk::Pending *pend = nullptr; uint64_t pend_cap = 0;
+    uint8_t *step_div = nullptr;
     unsigned long long *err = nullptr;
     uint32_t *counters = nullptr; uint64_t counters_cap = 0;
     uint32_t minus_one_id = 0xFFFFFFFFu;
@@ -62,6 +72,7 @@ struct zkpor_program {
     std::vector<uint32_t> h_hint_fn, h_hint_nout, h_hint_out; std::vector<uint64_t> h_hint_in0, h_hint_in1;
     uint64_t stats[4] = {0, 0, 0, 0};
     bool has_commit = false;
+    uint32_t narrow_max = zk::NARROW_MAX; int narrow_threads = zk::NARROW_THREADS; uint64_t wide_g32_max = zk::WIDE_G32_MAX;
     zk::DevBuf wires, abc;
 };
 
@@ -136,9 +147,13 @@ __device__ __forceinline__ Fr fr_from_words(const uint32_t *p) { Fr t; for (int 
 
 // hint functions except COUNT and COMMIT; lane 0 of the group runs them
 template <bool DRY>
-__device__ void exec_hint(const ProgView &v, uint32_t h) {
+__device__ void exec_hint(const ProgView &v, uint32_t h, uint64_t slot, uint64_t step) {
     const uint32_t fn = v.hint_fn[h], param = v.hint_param[h], out = v.hint_out[h], n_out = v.hint_nout[h];
-    if (DRY) { for (uint32_t k = 0; k < n_out; k++) v.solved[out + k] = 1; return; }
+    if (DRY) {
+        for (uint32_t k = 0; k < n_out; k++) v.solved[out + k] = 1;
+        if (fn == ZKPOR_HINT_INVZERO && step != NO_SLOT) v.step_div[step] = 1;
+        return;
+    }
     const uint64_t r0 = v.hint_in0[h], r1 = v.hint_in1[h];
     switch (fn) {
     case ZKPOR_HINT_DIVMOD: {
@@ -154,7 +169,10 @@ __device__ void exec_hint(const ProgView &v, uint32_t h) {
         for (uint32_t k = 0; k < n_out; k++) v.w[out + k] = (k < 256 && ((x.l[k >> 5] >> (k & 31)) & 1u)) ? Fr::one() : Fr::zero();
         break;
     }
-    case ZKPOR_HINT_INVZERO: v.w[out] = Fr::inv(aux_eval(v, r0)); break;
+    case ZKPOR_HINT_INVZERO:
+        if (slot != NO_SLOT) { Pending &pd = v.pend[slot]; pd.num = Fr::one(); pd.den = aux_eval(v, r0); pd.wire = out; pd.state = 2; }
+        else v.w[out] = Fr::inv(aux_eval(v, r0));
+        break;
     case ZKPOR_HINT_DECOMPOSE: {
         const Fr x = Fr::from_mont(aux_eval(v, r0));
         for (uint32_t k = 0; k < n_out; k++) {
@@ -192,10 +210,11 @@ __device__ void exec_hint(const ProgView &v, uint32_t h) {
 }
 
 // one instruction by a group of G lanes (lane = index in the group, mask = the group's lanes)
+// slot: where a division is parked for k_solve_div (wide levels), NO_SLOT = divide in place (narrow runs); step: the schedule step (dry run)
 template <int G, bool DRY>
-__device__ __forceinline__ void exec_instr(const ProgView &v, uint32_t packed, int lane, unsigned mask) {
+__device__ __forceinline__ void exec_instr(const ProgView &v, uint32_t packed, int lane, unsigned mask, uint64_t slot, uint64_t step) {
     if (packed & HINT_BIT) {
-        if (lane == 0) exec_hint<DRY>(v, packed & ~HINT_BIT);
+        if (lane == 0) exec_hint<DRY>(v, packed & ~HINT_BIT, slot, step);
         return;
     }
     const uint64_t row = packed;
@@ -210,7 +229,12 @@ __device__ __forceinline__ void exec_instr(const ProgView &v, uint32_t packed, i
         for (int off = G / 2; off > 0; off >>= 1) total += __shfl_xor_sync(mask, total, off, G);
         if (total > 1) { if (lane == 0) solve_fail(v, SE_UNSOLVED, row); return; }
         if (total == 0) { if (lane == 0) v.solve_e[row] = SOLVE_NONE; return; }
-        if (found) { v.solve_e[row] = cand; v.solved[v.wire[cand >> 62][cand & ((1ull << 62) - 1)]] = 1; }
+        if (found) {
+            const int side = (int)(cand >> 62); const uint64_t pos = cand & ((1ull << 62) - 1);
+            v.solve_e[row] = cand; v.solved[v.wire[side][pos]] = 1;
+            const uint32_t cid = v.coef[side][pos];
+            if (step != NO_SLOT && (side != 2 || (cid != v.one_id && cid != v.minus_one_id))) v.step_div[step] = 1;
+        }
         return;
     }
     const uint64_t se = v.solve_e[row];
@@ -234,26 +258,89 @@ __device__ __forceinline__ void exec_instr(const ProgView &v, uint32_t packed, i
         den = cid == v.one_id ? other : Fr::mul(v.coeffs[cid], other);
         if (den.is_zero()) { solve_fail(v, SE_DIV0, row); return; }
     }
-    Fr x = unit ? num : (neg ? Fr::neg(num) : Fr::mul(num, Fr::inv(den)));
-    v.w[v.wire[side][pos]] = x;
+    const uint32_t wire = v.wire[side][pos];
+    if (unit) v.w[wire] = num;
+    else if (neg) v.w[wire] = Fr::neg(num);
+    else if (slot != NO_SLOT) { Pending &pd = v.pend[slot]; pd.num = num; pd.den = den; pd.wire = wire; pd.state = 1; }
+    else v.w[wire] = Fr::mul(num, Fr::inv(den));
 }
 
 template <int G, bool DRY>
-__global__ void __launch_bounds__(256) k_solve_wide(ProgView v, uint64_t pos0, uint64_t count) {
+__global__ void __launch_bounds__(256) k_solve_wide(ProgView v, uint64_t pos0, uint64_t count, uint64_t step) {
     const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (g >= count) return;                               // whole groups leave together (G divides the block size)
     const int lane = threadIdx.x & (G - 1);
     const unsigned mask = (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << ((threadIdx.x & 31) & ~(G - 1));
-    exec_instr<G, DRY>(v, v.sched[pos0 + g], lane, mask);
+    exec_instr<G, DRY>(v, v.sched[pos0 + g], lane, mask, g, step);
 }
 
-// levels [l0, l1), each at most a few dozen instructions: one CTA, a warp per instruction, a barrier per level
+// The divisions of a wide level, one thread per DIV_BATCH consecutive slots sharing one inversion (Montgomery's trick): an inversion is
+// ~23 K instructions of one lane; done by the evaluating group it would idle the group's other lanes for all of them.
+static const int DIV_BATCH = 8;
+__global__ void __launch_bounds__(128) k_solve_div(ProgView v, uint64_t count) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, s0 = t * DIV_BATCH;
+    if (s0 >= count) return;
+    Fr pre[DIV_BATCH];
+    uint32_t st[DIV_BATCH];
+    Fr acc = Fr::one();
+#pragma unroll
+    for (int k = 0; k < DIV_BATCH; k++) {
+        st[k] = s0 + k < count ? v.pend[s0 + k].state : 0;
+        pre[k] = acc;
+        if (st[k]) {
+            const Fr d = v.pend[s0 + k].den;
+            if (d.is_zero()) { if (st[k] == 1) solve_fail(v, SE_DIV0, s0 + k); st[k] |= 4; }
+            else acc = Fr::mul(acc, d);
+        }
+    }
+    Fr inv = Fr::inv(acc);
+#pragma unroll
+    for (int k = DIV_BATCH - 1; k >= 0; k--) {
+        if (!st[k]) continue;
+        Pending &pd = v.pend[s0 + k];
+        if (st[k] & 4) v.w[pd.wire] = Fr::zero();
+        else { v.w[pd.wire] = Fr::mul(pd.num, Fr::mul(inv, pre[k])); inv = Fr::mul(inv, pd.den); }
+        pd.state = 0;
+    }
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// levels [l0, l1), each at most a few dozen instructions: one CTA, a warp per instruction, a barrier per level.
+// A level's critical path would be four dependent global loads (schedule entry -> row pointers -> term lists -> wire values) plus
+// the arithmetic; the first three are static data, so every warp pulls them into L1 ahead of time: the schedule entries of level
+// l+3, the row pointers of level l+2 and the term lists of level l+1 while level l is being solved.  What remains per level is one
+// L2 round trip for the wire values the previous level has just written.
 template <bool DRY>
 __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow(ProgView v, uint64_t l0, uint64_t l1) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (uint64_t l = l0; l < l1; l++) {
+        if (l + 3 < l1) {
+            const uint64_t s0 = v.lvl_start[l + 3], s1 = v.lvl_start[l + 4];
+            for (uint64_t p = s0 + (uint64_t)threadIdx.x * 32; p < s1; p += (uint64_t)blockDim.x * 32) prefetch_l1(v.sched + p);
+        }
+        if (l + 2 < l1) {
+            const uint64_t s0 = v.lvl_start[l + 2], s1 = v.lvl_start[l + 3];
+            for (uint64_t p = s0 + warp; p < s1; p += nwarps) {
+                const uint32_t packed = v.sched[p];
+                if (packed & HINT_BIT) { if (lane == 0) { prefetch_l1(v.hint_in0 + (packed & ~HINT_BIT)); prefetch_l1(v.hint_out + (packed & ~HINT_BIT)); } }
+                else if (lane < 3) prefetch_l1(v.ptr[lane] + packed);
+                else if (lane == 3) prefetch_l1(v.solve_e + packed);
+            }
+        }
+        if (l + 1 < l1) {
+            const uint64_t s0 = v.lvl_start[l + 1], s1 = v.lvl_start[l + 2];
+            for (uint64_t p = s0 + warp; p < s1; p += nwarps) {
+                const uint32_t packed = v.sched[p];
+                if (packed & HINT_BIT) continue;
+                for (int side = 0; side < 3; side++) {
+                    const uint64_t e0 = v.ptr[side][packed], e1 = v.ptr[side][packed + 1];
+                    for (uint64_t e = (e0 & ~31ull) + (uint64_t)lane * 32; e < e1; e += 32 * 32) { prefetch_l1(v.wire[side] + e); prefetch_l1(v.coef[side] + e); }
+                }
+            }
+        }
         const uint64_t s0 = v.lvl_start[l], s1 = v.lvl_start[l + 1];
-        for (uint64_t p = s0 + warp; p < s1; p += nwarps) exec_instr<32, DRY>(v, v.sched[p], lane, 0xFFFFFFFFu);
+        for (uint64_t p = s0 + warp; p < s1; p += nwarps) exec_instr<32, DRY>(v, v.sched[p], lane, 0xFFFFFFFFu, NO_SLOT, NO_SLOT);
         __syncthreads();
     }
 }
@@ -302,6 +389,7 @@ static ProgView make_view(zkpor_program *p, Fr *w, uint8_t *solved) {
     v.sched = p->sched; v.lvl_start = p->lvl_start;
     v.hint_fn = p->hint_fn; v.hint_param = p->hint_param; v.hint_out = p->hint_out; v.hint_nout = p->hint_nout; v.hint_in0 = p->hint_in0; v.hint_in1 = p->hint_in1;
     v.table_ptr = p->table_ptr; v.solve_e = p->solve_e; v.w = w; v.solved = solved; v.err = p->err;
+    v.pend = p->pend; v.step_div = p->step_div;
     return v;
 }
 
@@ -322,16 +410,26 @@ template <bool DRY>
 static int32_t run_schedule(zkpor_ctx *ctx, zkpor_program *p, zkpor_pk *pk, Fr *w, uint8_t *solved, G1XYZZ *commit, G1XYZZ *pok) {
     ProgView v = make_view(p, w, solved);
     ZK_CUDA(cudaMemsetAsync(p->err, 0, 8, ctx->stream));
-    for (const Step &s : p->steps) {
+    for (size_t si = 0; si < p->steps.size(); si++) {
+        const Step &s = p->steps[si];
         switch (s.kind) {
         case STEP_WIDE: {
+            // a level of a few thousand instructions cannot fill the GPU either way: a whole warp per instruction shortens the
+            // serial part (a Poseidon row has up to ~80 terms per side); big levels take 8 lanes per instruction
             const uint64_t count = s.b - s.a;
-            ZK_LAUNCH(ctx, (k_solve_wide<8, DRY>), grid_for(count * 8, 256), 256, 0, v, s.a, count);
+            KTimed kt(ctx, KC_SOLVE_WIDE, DRY ? 0 : count);
+            if (count <= p->wide_g32_max) ZK_LAUNCH(ctx, (k_solve_wide<32, DRY>), grid_for(count * 32, 256), 256, 0, v, s.a, count, (uint64_t)si);
+            else ZK_LAUNCH(ctx, (k_solve_wide<8, DRY>), grid_for(count * 8, 256), 256, 0, v, s.a, count, (uint64_t)si);
+            if (!DRY && s.has_div) ZK_LAUNCH(ctx, k_solve_div, grid_for((count + DIV_BATCH - 1) / DIV_BATCH, 128), 128, 0, v, count);
+            kt.stop();
             break;
         }
-        case STEP_NARROW:
-            ZK_LAUNCH(ctx, k_solve_narrow<DRY>, 1, NARROW_THREADS, 0, v, s.a, s.b);
+        case STEP_NARROW: {
+            KTimed kt(ctx, KC_SOLVE_NARROW, DRY ? 0 : s.b - s.a);
+            ZK_LAUNCH(ctx, k_solve_narrow<DRY>, 1, p->narrow_threads, 0, v, s.a, s.b);
+            kt.stop();
             break;
+        }
         case STEP_COUNT: {
             const uint32_t h = (uint32_t)s.a, n_out = p->h_hint_nout[h], out = p->h_hint_out[h];
             if (DRY) { ZK_LAUNCH(ctx, k_mark_solved, grid_for(n_out, 256), 256, 0, solved, (uint64_t)out, (uint64_t)n_out); break; }
@@ -390,7 +488,7 @@ int32_t zkpor_program_free(zkpor_ctx *ctx, zkpor_program *p) {
     if (!p) return ZKPOR_OK;
     if (p->cs) zkpor_r1cs_free(ctx, p->cs);
     void *ptrs[] = {p->aux_ptr, p->aux_wire, p->aux_coef, p->sched, p->lvl_start, p->hint_fn, p->hint_param, p->hint_out, p->hint_nout,
-                    p->hint_in0, p->hint_in1, p->table_ptr, p->solve_e, p->err, p->counters};
+                    p->hint_in0, p->hint_in1, p->table_ptr, p->solve_e, p->err, p->counters, p->pend, p->step_div};
     for (void *q : ptrs) if (q) cudaFree(q);
     p->wires.release(); p->abc.release();
     delete p;
@@ -454,12 +552,15 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
         if (fn == ZKPOR_HINT_COMMIT) { if (p->h_hint_nout[h] != 1) return bad("COMMIT hint has one output"); p->has_commit = true; }
     }
     for (uint64_t t = 0; t < d->n_tables; t++) if (tptr[t] > tptr[t + 1] || tptr[t + 1] > d->n_aux_rows) return bad("table_ptr out of range");
+    if (const char *e = getenv("ZKPOR_NARROW_MAX")) p->narrow_max = (uint32_t)std::max(1, atoi(e));
+    if (const char *e = getenv("ZKPOR_NARROW_THREADS")) p->narrow_threads = std::min(NARROW_THREADS, std::max(32, atoi(e) & ~31));
+    if (const char *e = getenv("ZKPOR_WIDE_G32_MAX")) p->wide_g32_max = (uint64_t)std::max(0, atoi(e));
     // schedule: instructions in level order, special hints lifted out as steps of their own
     std::vector<uint32_t> sched; sched.reserve(d->n_instr);
     std::vector<uint64_t> lvl_start; lvl_start.reserve(d->n_levels + 1);
     int64_t run_first = -1;
     auto close_run = [&](uint64_t end_level) {
-        if (run_first >= 0) { p->steps.push_back({STEP_NARROW, (uint64_t)run_first, end_level}); p->stats[1]++; p->stats[2] += end_level - run_first; run_first = -1; }
+        if (run_first >= 0) { p->steps.push_back({STEP_NARROW, (uint64_t)run_first, end_level, false}); p->stats[1]++; p->stats[2] += end_level - run_first; run_first = -1; }
     };
     for (uint64_t l = 0; l < d->n_levels; l++) {
         lvl_start.push_back(sched.size());
@@ -473,14 +574,14 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
             if (fn == ZKPOR_HINT_COUNT || fn == ZKPOR_HINT_COMMIT) {
                 if (!special) close_run(l);
                 special = true;
-                p->steps.push_back({fn == ZKPOR_HINT_COUNT ? STEP_COUNT : STEP_COMMIT, arg[ins], 0});
+                p->steps.push_back({fn == ZKPOR_HINT_COUNT ? STEP_COUNT : STEP_COMMIT, arg[ins], 0, false});
                 if (fn == ZKPOR_HINT_COUNT) p->stats[3]++;
             } else sched.push_back(arg[ins] | HINT_BIT);
         }
         const uint64_t n_l = sched.size() - lvl_start.back();
         if (n_l == 0) continue;
-        if (n_l <= NARROW_MAX) { if (run_first < 0) run_first = (int64_t)l; }
-        else { close_run(l); p->steps.push_back({STEP_WIDE, lvl_start.back(), (uint64_t)sched.size()}); p->stats[0]++; }
+        if (n_l <= p->narrow_max) { if (run_first < 0) run_first = (int64_t)l; }
+        else { close_run(l); p->steps.push_back({STEP_WIDE, lvl_start.back(), (uint64_t)sched.size(), false}); p->stats[0]++; p->pend_cap = std::max<uint64_t>(p->pend_cap, n_l); }
     }
     lvl_start.push_back(sched.size());
     close_run(d->n_levels);
@@ -496,6 +597,10 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
     p->counters_cap = max_out;
     if (cudaMalloc((void **)&p->solve_e, std::max<uint64_t>(d->n_constraints, 1) * 8) != cudaSuccess || cudaMalloc((void **)&p->err, 8) != cudaSuccess ||
         cudaMalloc((void **)&p->counters, max_out * 4) != cudaSuccess) { set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
+    if (cudaMalloc((void **)&p->pend, std::max<uint64_t>(p->pend_cap, 1) * sizeof(Pending)) != cudaSuccess ||
+        cudaMalloc((void **)&p->step_div, p->steps.size() + 1) != cudaSuccess) { set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
+    cudaMemsetAsync(p->pend, 0, std::max<uint64_t>(p->pend_cap, 1) * sizeof(Pending), ctx->stream);
+    cudaMemsetAsync(p->step_div, 0, p->steps.size() + 1, ctx->stream);
     // dry run: which wire does every R1C instruction solve for
     uint8_t *solved = nullptr;
     if (cudaMalloc((void **)&solved, d->n_wires) != cudaSuccess) { set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
@@ -503,6 +608,11 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
     cudaMemsetAsync(solved, 1, d->n_public + d->n_secret, ctx->stream);
     cudaMemsetAsync(p->solve_e, 0xFF, std::max<uint64_t>(d->n_constraints, 1) * 8, ctx->stream);
     rc = run_schedule<true>(ctx, p, nullptr, nullptr, solved, nullptr, nullptr);
+    if (rc == ZKPOR_OK) {
+        std::vector<uint8_t> sd;
+        rc = fetch(sd, (const uint8_t *)p->step_div, p->steps.size());
+        if (rc == ZKPOR_OK) for (size_t i = 0; i < p->steps.size(); i++) p->steps[i].has_div = sd[i] != 0;
+    }
     if (rc == ZKPOR_OK) {
         // every wire must have been reached
         std::vector<uint8_t> hs;
@@ -520,7 +630,7 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
 int32_t zkpor_r1cs_solve(zkpor_ctx *ctx, zkpor_program *prog, zkpor_pk *pk, const void *inputs, void *out_wires, void *out_a, void *out_b,
                          void *out_c, void *out_commitment64) {
     ZK_REQUIRE(ctx && prog && inputs, "r1cs_solve: null argument");
-    ZK_REQUIRE(!pk || pk->n_wires == prog->n_wires, "r1cs_solve: the program and the key disagree on the number of wires");
+    ZK_REQUIRE(!pk || pk->n_wires_total == prog->n_wires, "r1cs_solve: the program and the key disagree on the number of wires");
     ZK_CUDA(cudaSetDevice(ctx->device));
     stages_reset(ctx);
     Fr *w;
