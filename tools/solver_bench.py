@@ -1,6 +1,6 @@
 """Witness-solver timing on one B200 (development tool): builds the bench circuit at 2^LOG_N and times zkpor_r1cs_solve alone for a
 few schedule settings (env knobs of csrc/solver.cu), with the per-class launch statistics of the library.
-Usage: python tools/solver_bench.py [log_n] [settings...]   setting = NARROW_MAX:NARROW_THREADS:WIDE_G32_MAX"""
+Usage: python tools/solver_bench.py [log_n] [settings...]   setting = NARROW_MAX:NARROW_THREADS:WIDE_LONG_ROW (0 = a warp for every row)"""
 import json
 import os
 import sys
@@ -17,7 +17,7 @@ import zkpor_b200 as zk
 
 def main():
     log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 22
-    settings = sys.argv[2:] or ["96:1024:32768", "96:512:32768", "96:1024:0", "32:1024:32768", "512:1024:32768"]
+    settings = sys.argv[2:] or ["96:512:9", "96:512:0", "96:512:17", "96:256:9", "24:512:9"]
     ctx = zk.Context(0)
     wl = bench.Workload(torch, zk, ctx, log_n)
     print(wl.describe(), "setup %.1f s" % wl.setup_s, flush=True)
@@ -25,7 +25,7 @@ def main():
     out = []
     for st in settings:
         nm, nt, g32 = st.split(":")
-        os.environ["ZKPOR_NARROW_MAX"], os.environ["ZKPOR_NARROW_THREADS"], os.environ["ZKPOR_WIDE_G32_MAX"] = nm, nt, g32
+        os.environ["ZKPOR_NARROW_MAX"], os.environ["ZKPOR_NARROW_THREADS"], os.environ["ZKPOR_WIDE_LONG_ROW"] = nm, nt, g32
         t0 = time.perf_counter()
         prog = zk.Program(ctx, wl.flat)
         up = time.perf_counter() - t0

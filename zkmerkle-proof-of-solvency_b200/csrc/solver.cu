@@ -27,13 +27,12 @@ using namespace ec;
 namespace zk {
 
 static const uint32_t NARROW_MAX = 96;          // levels up to this many instructions are fused into single-CTA runs (env ZKPOR_NARROW_MAX)
-static const int NARROW_THREADS = 1024;         // upper bound of the fused-run CTA (env ZKPOR_NARROW_THREADS picks fewer warps)
-static const uint64_t WIDE_G32_MAX = 1u << 15;  // wide levels up to this many instructions take a whole warp per instruction (env ZKPOR_WIDE_G32_MAX)
+static const int NARROW_THREADS = 512;          // upper bound of the fused-run CTA (env ZKPOR_NARROW_THREADS picks fewer warps)
 static const uint64_t SOLVE_NONE = ~0ull;
 static const uint32_t HINT_BIT = 0x80000000u;
 
 enum StepKind { STEP_WIDE = 0, STEP_NARROW, STEP_COUNT, STEP_COMMIT };
-struct Step { int kind; uint64_t a, b; bool has_div; };   // WIDE: sched range [a, b); NARROW: levels [a, b); COUNT / COMMIT: hint id a
+struct Step { int kind; uint64_t a, b; bool has_div; uint64_t n_long; };   // WIDE: sched range [a, b), the first n_long rows long; NARROW: levels [a, b); COUNT / COMMIT: hint id a
 enum SolveErr { SE_OK = 0, SE_UNSOLVED = 1, SE_DIV0 = 2, SE_INDEX = 3, SE_HINT = 4 };
 
 struct Pending;
@@ -70,9 +69,9 @@ struct zkpor_program {
     uint32_t minus_one_id = 0xFFFFFFFFu;
     std::vector<zk::Step> steps;
     std::vector<uint32_t> h_hint_fn, h_hint_nout, h_hint_out; std::vector<uint64_t> h_hint_in0, h_hint_in1;
-    uint64_t stats[4] = {0, 0, 0, 0};
+    uint64_t stats[4] = {0, 0, 0, 0}, stats_long = 0;
     bool has_commit = false;
-    uint32_t narrow_max = zk::NARROW_MAX; int narrow_threads = zk::NARROW_THREADS; uint64_t wide_g32_max = zk::WIDE_G32_MAX;
+    uint32_t narrow_max = zk::NARROW_MAX; int narrow_threads = zk::NARROW_THREADS; uint32_t long_row = 0;
     zk::DevBuf wires, abc;
 };
 
@@ -89,16 +88,9 @@ __device__ __forceinline__ Fr term_acc(const ProgView &v, const Fr &acc, uint32_
     return Fr::add(acc, Fr::mul(v.coeffs[cid], x));
 }
 
-// sum over the terms of row `row` except position `skip`, the G lanes of a group taking every G-th term; valid on lane 0
+// tree sum over the G lanes of a group; valid on lane 0
 template <int G>
-__device__ __forceinline__ Fr group_dot(const ProgView &v, const uint64_t *ptr, const uint32_t *wire, const uint32_t *coef, uint64_t row,
-                                        uint64_t skip, int lane, unsigned mask) {
-    Fr acc = Fr::zero();
-    const uint64_t e1 = ptr[row + 1];
-    for (uint64_t e = ptr[row] + lane; e < e1; e += G) {
-        if (e == skip) continue;
-        acc = term_acc(v, acc, coef[e], v.w[wire[e]]);
-    }
+__device__ __forceinline__ Fr group_sum(Fr acc, unsigned mask) {
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) {
         Fr o;
@@ -107,6 +99,25 @@ __device__ __forceinline__ Fr group_dot(const ProgView &v, const uint64_t *ptr, 
         acc = Fr::add(acc, o);
     }
     return acc;
+}
+
+// sum over the terms of row `row` except position `skip`, lane `lane` of `stride` lanes taking every stride-th term (partial sum of the lane)
+__device__ __forceinline__ Fr lane_dot(const ProgView &v, const uint64_t *ptr, const uint32_t *wire, const uint32_t *coef, uint64_t row, uint64_t skip,
+                                       int lane, int stride) {
+    Fr acc = Fr::zero();
+    const uint64_t e1 = ptr[row + 1];
+    for (uint64_t e = ptr[row] + lane; e < e1; e += stride) {
+        if (e == skip) continue;
+        acc = term_acc(v, acc, coef[e], v.w[wire[e]]);
+    }
+    return acc;
+}
+
+// the same sum by the G lanes of a group; valid on lane 0
+template <int G>
+__device__ __forceinline__ Fr group_dot(const ProgView &v, const uint64_t *ptr, const uint32_t *wire, const uint32_t *coef, uint64_t row,
+                                        uint64_t skip, int lane, unsigned mask) {
+    return group_sum<G>(lane_dot(v, ptr, wire, coef, row, skip, lane, G), mask);
 }
 
 __device__ __forceinline__ Fr aux_eval(const ProgView &v, uint64_t row) {
@@ -209,6 +220,28 @@ __device__ void exec_hint(const ProgView &v, uint32_t h, uint64_t slot, uint64_t
     }
 }
 
+// the unknown wire of constraint `row` (term `pos` of side `side`) from the known parts a, b, c of the three sides; one lane
+__device__ __forceinline__ void finish_instr(const ProgView &v, uint64_t row, int side, uint64_t pos, const Fr &a, const Fr &b, const Fr &c, uint64_t slot) {
+    const uint32_t cid = v.coef[side][pos];
+    Fr num, den;
+    bool unit = false, neg = false;
+    if (side == 2) {                                      // L*R = known + cf*x
+        num = Fr::sub(Fr::mul(a, b), c);
+        unit = cid == v.one_id; neg = cid == v.minus_one_id;
+        den = v.coeffs[cid];
+    } else {                                              // (known + cf*x) * other = c
+        const Fr &known = side == 0 ? a : b, &other = side == 0 ? b : a;
+        num = Fr::sub(c, Fr::mul(known, other));
+        den = cid == v.one_id ? other : Fr::mul(v.coeffs[cid], other);
+        if (den.is_zero()) { solve_fail(v, SE_DIV0, row); return; }
+    }
+    const uint32_t wire = v.wire[side][pos];
+    if (unit) v.w[wire] = num;
+    else if (neg) v.w[wire] = Fr::neg(num);
+    else if (slot != NO_SLOT) { Pending &pd = v.pend[slot]; pd.num = num; pd.den = den; pd.wire = wire; pd.state = 1; }
+    else v.w[wire] = Fr::mul(num, Fr::inv(den));
+}
+
 // one instruction by a group of G lanes (lane = index in the group, mask = the group's lanes)
 // slot: where a division is parked for k_solve_div (wide levels), NO_SLOT = divide in place (narrow runs); step: the schedule step (dry run)
 template <int G, bool DRY>
@@ -245,33 +278,39 @@ __device__ __forceinline__ void exec_instr(const ProgView &v, uint32_t packed, i
     const Fr b = group_dot<G>(v, v.ptr[1], v.wire[1], v.coef[1], row, side == 1 ? pos : SOLVE_NONE, lane, mask);
     const Fr c = group_dot<G>(v, v.ptr[2], v.wire[2], v.coef[2], row, side == 2 ? pos : SOLVE_NONE, lane, mask);
     if (lane != 0) return;
-    const uint32_t cid = v.coef[side][pos];
-    Fr num, den;
-    bool unit = false, neg = false;
-    if (side == 2) {                                      // L*R = known + cf*x
-        num = Fr::sub(Fr::mul(a, b), c);
-        unit = cid == v.one_id; neg = cid == v.minus_one_id;
-        den = v.coeffs[cid];
-    } else {                                              // (known + cf*x) * other = c
-        const Fr &known = side == 0 ? a : b, &other = side == 0 ? b : a;
-        num = Fr::sub(c, Fr::mul(known, other));
-        den = cid == v.one_id ? other : Fr::mul(v.coeffs[cid], other);
-        if (den.is_zero()) { solve_fail(v, SE_DIV0, row); return; }
-    }
-    const uint32_t wire = v.wire[side][pos];
-    if (unit) v.w[wire] = num;
-    else if (neg) v.w[wire] = Fr::neg(num);
-    else if (slot != NO_SLOT) { Pending &pd = v.pend[slot]; pd.num = num; pd.den = den; pd.wire = wire; pd.state = 1; }
-    else v.w[wire] = Fr::mul(num, Fr::inv(den));
+    finish_instr(v, row, side, pos, a, b, c, slot);
 }
 
-template <int G, bool DRY>
-__global__ void __launch_bounds__(256) k_solve_wide(ProgView v, uint64_t pos0, uint64_t count, uint64_t step) {
-    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    if (g >= count) return;                               // whole groups leave together (G divides the block size)
-    const int lane = threadIdx.x & (G - 1);
-    const unsigned mask = (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << ((threadIdx.x & 31) & ~(G - 1));
-    exec_instr<G, DRY>(v, v.sched[pos0 + g], lane, mask, g, step);
+// One wide level.  Its instructions are ordered long rows first (zkpor_program_upload): the first n_long take a whole warp each -- a
+// Poseidon row has ~80 terms per side, one product per lane -- the others (one to eight terms per side: most of a compiled circuit)
+// WIDE_GS lanes each, so that a level of 10^5 short rows is a few hundred CTAs instead of 10^4.
+static const int WIDE_GS = 4;
+static const uint32_t WIDE_LONG_ROW = 9;          // terms on the longest side from which a row counts as long
+template <bool DRY>
+__global__ void __launch_bounds__(256) k_solve_wide(ProgView v, uint64_t pos0, uint64_t n_long, uint64_t count, uint64_t step) {
+    const uint64_t long_blocks = (n_long + 7) / 8;
+    if (blockIdx.x < long_blocks) {
+        const uint64_t g = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+        if (g >= n_long) return;
+        exec_instr<32, DRY>(v, v.sched[pos0 + g], threadIdx.x & 31, 0xFFFFFFFFu, g, step);
+    } else {
+        const uint64_t g = n_long + ((uint64_t)(blockIdx.x - long_blocks) * 256 + threadIdx.x) / WIDE_GS;
+        if (g >= count) return;                           // whole groups leave together (WIDE_GS divides the block size)
+        const int lane = threadIdx.x & (WIDE_GS - 1);
+        const unsigned mask = ((1u << WIDE_GS) - 1u) << ((threadIdx.x & 31) & ~(WIDE_GS - 1));
+        exec_instr<WIDE_GS, DRY>(v, v.sched[pos0 + g], lane, mask, g, step);
+    }
+}
+
+// sched[i] -> the longest side of its constraint row (hints: 0), capped at 255: the upload orders a wide level by it
+__global__ void k_row_class(ProgView v, uint64_t n, uint8_t *cls) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t packed = v.sched[i];
+    uint64_t m = 0;
+    if (!(packed & HINT_BIT))
+        for (int side = 0; side < 3; side++) m = max(m, v.ptr[side][(uint64_t)packed + 1] - v.ptr[side][packed]);
+    cls[i] = (uint8_t)min(m, (uint64_t)255);
 }
 
 // The divisions of a wide level, one thread per DIV_BATCH consecutive slots sharing one inversion (Montgomery's trick): an inversion is
@@ -306,13 +345,21 @@ __global__ void __launch_bounds__(128) k_solve_div(ProgView v, uint64_t count) {
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// levels [l0, l1), each at most a few dozen instructions: one CTA, a warp per instruction, a barrier per level.
+// levels [l0, l1), each at most a few dozen instructions: one CTA, a barrier per level.
 // A level's critical path would be four dependent global loads (schedule entry -> row pointers -> term lists -> wire values) plus
 // the arithmetic; the first three are static data, so every warp pulls them into L1 ahead of time: the schedule entries of level
 // l+3, the row pointers of level l+2 and the term lists of level l+1 while level l is being solved.  What remains per level is one
-// L2 round trip for the wire values the previous level has just written.
+// L2 round trip for the wire values the previous level has just written, and the arithmetic -- which for ONE warp per instruction
+// is a latency chain of its own: a field product is ~250 dependent instructions of a lane (~800 cycles with nothing else to issue),
+// and an 80-term Poseidon row makes every lane do three of them per side, three sides in sequence.  The serial sponge tail of the
+// circuit has one or two instructions per level, so the CTA's other warps are idle: there, the three sides of an instruction go to
+// different warps and a side's terms to up to NARROW_SUB warps (one product per lane), the partial sums meet in shared memory, and
+// one lane finishes (a*b, the subtraction, the store).  Two barriers per level instead of one, a third of the dependent products.
+static const int NARROW_SUB = 4;                  // warps per side at most
+static const int NARROW_SPLIT_INSTR = NARROW_THREADS / 32 / 3;   // instructions of a level that can be split by side
 template <bool DRY>
 __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow(ProgView v, uint64_t l0, uint64_t l1) {
+    __shared__ Fr part[NARROW_SPLIT_INSTR][3][NARROW_SUB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (uint64_t l = l0; l < l1; l++) {
         if (l + 3 < l1) {
@@ -340,7 +387,35 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow(ProgView v, uin
             }
         }
         const uint64_t s0 = v.lvl_start[l], s1 = v.lvl_start[l + 1];
-        for (uint64_t p = s0 + warp; p < s1; p += nwarps) exec_instr<32, DRY>(v, v.sched[p], lane, 0xFFFFFFFFu, NO_SLOT, NO_SLOT);
+        const int k = (int)(s1 - s0);
+        const int sub = DRY || 3 * k > nwarps ? 0 : min(NARROW_SUB, nwarps / (3 * k));
+        if (sub == 0) {
+            for (uint64_t p = s0 + warp; p < s1; p += nwarps) exec_instr<32, DRY>(v, v.sched[p], lane, 0xFFFFFFFFu, NO_SLOT, NO_SLOT);
+            __syncthreads();
+            continue;
+        }
+        // split mode: warp -> (instruction, side, part)
+        const int per = 3 * sub, ins = warp / per, rem = warp - ins * per, side = rem / sub, prt = rem - side * sub;
+        uint32_t packed = HINT_BIT;
+        uint64_t se = SOLVE_NONE;
+        if (ins < k) {
+            packed = v.sched[s0 + ins];
+            if (packed & HINT_BIT) { if (rem == 0 && lane == 0) exec_hint<false>(v, packed & ~HINT_BIT, NO_SLOT, NO_SLOT); }
+            else {
+                se = v.solve_e[packed];
+                if (se != SOLVE_NONE) {
+                    const uint64_t skip = (int)(se >> 62) == side ? (se & ((1ull << 62) - 1)) : SOLVE_NONE;
+                    const Fr acc = group_sum<32>(lane_dot(v, v.ptr[side], v.wire[side], v.coef[side], packed, skip, prt * 32 + lane, sub * 32), 0xFFFFFFFFu);
+                    if (lane == 0) part[ins][side][prt] = acc;
+                }
+            }
+        }
+        __syncthreads();
+        if (ins < k && rem == 0 && lane == 0 && !(packed & HINT_BIT) && se != SOLVE_NONE) {
+            Fr abc[3];
+            for (int sd = 0; sd < 3; sd++) { abc[sd] = part[ins][sd][0]; for (int q = 1; q < sub; q++) abc[sd] = Fr::add(abc[sd], part[ins][sd][q]); }
+            finish_instr(v, packed, (int)(se >> 62), se & ((1ull << 62) - 1), abc[0], abc[1], abc[2], NO_SLOT);
+        }
         __syncthreads();
     }
 }
@@ -414,12 +489,9 @@ static int32_t run_schedule(zkpor_ctx *ctx, zkpor_program *p, zkpor_pk *pk, Fr *
         const Step &s = p->steps[si];
         switch (s.kind) {
         case STEP_WIDE: {
-            // a level of a few thousand instructions cannot fill the GPU either way: a whole warp per instruction shortens the
-            // serial part (a Poseidon row has up to ~80 terms per side); big levels take 8 lanes per instruction
-            const uint64_t count = s.b - s.a;
+            const uint64_t count = s.b - s.a, blocks = (s.n_long + 7) / 8 + (((count - s.n_long) * WIDE_GS + 255) / 256);
             KTimed kt(ctx, KC_SOLVE_WIDE, DRY ? 0 : count);
-            if (count <= p->wide_g32_max) ZK_LAUNCH(ctx, (k_solve_wide<32, DRY>), grid_for(count * 32, 256), 256, 0, v, s.a, count, (uint64_t)si);
-            else ZK_LAUNCH(ctx, (k_solve_wide<8, DRY>), grid_for(count * 8, 256), 256, 0, v, s.a, count, (uint64_t)si);
+            ZK_LAUNCH(ctx, k_solve_wide<DRY>, (int)blocks, 256, 0, v, s.a, s.n_long, count, (uint64_t)si);
             if (!DRY && s.has_div) ZK_LAUNCH(ctx, k_solve_div, grid_for((count + DIV_BATCH - 1) / DIV_BATCH, 128), 128, 0, v, count);
             kt.stop();
             break;
@@ -554,13 +626,14 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
     for (uint64_t t = 0; t < d->n_tables; t++) if (tptr[t] > tptr[t + 1] || tptr[t + 1] > d->n_aux_rows) return bad("table_ptr out of range");
     if (const char *e = getenv("ZKPOR_NARROW_MAX")) p->narrow_max = (uint32_t)std::max(1, atoi(e));
     if (const char *e = getenv("ZKPOR_NARROW_THREADS")) p->narrow_threads = std::min(NARROW_THREADS, std::max(32, atoi(e) & ~31));
-    if (const char *e = getenv("ZKPOR_WIDE_G32_MAX")) p->wide_g32_max = (uint64_t)std::max(0, atoi(e));
+    p->long_row = WIDE_LONG_ROW;
+    if (const char *e = getenv("ZKPOR_WIDE_LONG_ROW")) p->long_row = (uint32_t)std::max(0, atoi(e));   // 0: every row takes a warp
     // schedule: instructions in level order, special hints lifted out as steps of their own
     std::vector<uint32_t> sched; sched.reserve(d->n_instr);
     std::vector<uint64_t> lvl_start; lvl_start.reserve(d->n_levels + 1);
     int64_t run_first = -1;
     auto close_run = [&](uint64_t end_level) {
-        if (run_first >= 0) { p->steps.push_back({STEP_NARROW, (uint64_t)run_first, end_level, false}); p->stats[1]++; p->stats[2] += end_level - run_first; run_first = -1; }
+        if (run_first >= 0) { p->steps.push_back({STEP_NARROW, (uint64_t)run_first, end_level, false, 0}); p->stats[1]++; p->stats[2] += end_level - run_first; run_first = -1; }
     };
     for (uint64_t l = 0; l < d->n_levels; l++) {
         lvl_start.push_back(sched.size());
@@ -574,14 +647,14 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
             if (fn == ZKPOR_HINT_COUNT || fn == ZKPOR_HINT_COMMIT) {
                 if (!special) close_run(l);
                 special = true;
-                p->steps.push_back({fn == ZKPOR_HINT_COUNT ? STEP_COUNT : STEP_COMMIT, arg[ins], 0, false});
+                p->steps.push_back({fn == ZKPOR_HINT_COUNT ? STEP_COUNT : STEP_COMMIT, arg[ins], 0, false, 0});
                 if (fn == ZKPOR_HINT_COUNT) p->stats[3]++;
             } else sched.push_back(arg[ins] | HINT_BIT);
         }
         const uint64_t n_l = sched.size() - lvl_start.back();
         if (n_l == 0) continue;
         if (n_l <= p->narrow_max) { if (run_first < 0) run_first = (int64_t)l; }
-        else { close_run(l); p->steps.push_back({STEP_WIDE, lvl_start.back(), (uint64_t)sched.size(), false}); p->stats[0]++; p->pend_cap = std::max<uint64_t>(p->pend_cap, n_l); }
+        else { close_run(l); p->steps.push_back({STEP_WIDE, lvl_start.back(), (uint64_t)sched.size(), false, 0}); p->stats[0]++; p->pend_cap = std::max<uint64_t>(p->pend_cap, n_l); }
     }
     lvl_start.push_back(sched.size());
     close_run(d->n_levels);
@@ -601,6 +674,28 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
         cudaMalloc((void **)&p->step_div, p->steps.size() + 1) != cudaSuccess) { set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
     cudaMemsetAsync(p->pend, 0, std::max<uint64_t>(p->pend_cap, 1) * sizeof(Pending), ctx->stream);
     cudaMemsetAsync(p->step_div, 0, p->steps.size() + 1, ctx->stream);
+    // wide levels: long rows first (k_solve_wide gives them a warp each, the short ones WIDE_GS lanes)
+    {
+        uint8_t *d_cls = nullptr;
+        std::vector<uint8_t> cls;
+        if (cudaMalloc((void **)&d_cls, std::max<size_t>(sched.size(), 1)) != cudaSuccess) { set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
+        ProgView v0 = make_view(p, nullptr, nullptr);
+        k_row_class<<<grid_for(sched.size(), 256), 256, 0, ctx->stream>>>(v0, (uint64_t)sched.size(), d_cls);
+        rc = fetch(cls, (const uint8_t *)d_cls, sched.size());
+        cudaFree(d_cls);
+        if (rc != ZKPOR_OK) return fail(rc);
+        std::vector<uint32_t> tmp;
+        for (Step &st : p->steps) {
+            if (st.kind != STEP_WIDE) continue;
+            tmp.clear();
+            for (uint64_t i = st.a; i < st.b; i++) if (p->long_row == 0 || cls[i] >= p->long_row) tmp.push_back(sched[i]);
+            st.n_long = tmp.size();
+            for (uint64_t i = st.a; i < st.b; i++) if (!(p->long_row == 0 || cls[i] >= p->long_row)) tmp.push_back(sched[i]);
+            std::copy(tmp.begin(), tmp.end(), sched.begin() + st.a);
+            p->stats_long += st.n_long;
+        }
+        if (cudaMemcpy(p->sched, sched.data(), sched.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("program_upload: schedule copy failed"); return fail(ZKPOR_ERR_CUDA); }
+    }
     // dry run: which wire does every R1C instruction solve for
     uint8_t *solved = nullptr;
     if (cudaMalloc((void **)&solved, d->n_wires) != cudaSuccess) { set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
