@@ -59,7 +59,9 @@ const char *zkpor_stage_name(int32_t i);
 /* Per-launch timing of the dominant kernels (CUDA events on the context's stream around every launch of a class):
  * enable, run, then query.  klass: 0 = G1 bucket accumulation, 1 = G2 bucket accumulation, 2 = NTT butterfly pass,
  * 3 = digit/scatter (sort) kernels, 4 = Poseidon/Merkle kernels, 5 = solver wide-level launches, 6 = solver fused narrow runs.
- * units = terms (MSM), elements (NTT), hashes, instructions (5), levels (6). */
+ * units = terms (MSM), elements (NTT), hashes, instructions (5), levels (6).
+ * enable: 0 = off, 1 = every class, 1 | (mask << 8) = the classes whose bit is set in mask (an event pair per launch is not free:
+ * a proof has ~8 000 solver launches, so bench.py times only the classes it reports while the clock runs). */
 int32_t zkpor_ctx_kernel_timing(zkpor_ctx *ctx, int32_t enable);
 int32_t zkpor_ctx_kernel_stats(zkpor_ctx *ctx, int32_t klass, double *total_ms, uint64_t *launches, uint64_t *units);
 
@@ -204,6 +206,16 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *desc, zkp
 int32_t zkpor_program_free(zkpor_ctx *ctx, zkpor_program *prog);
 /* number of schedule steps by type: wide level launches, fused runs of narrow levels, levels inside those runs, count hints */
 int32_t zkpor_program_stats(zkpor_program *prog, uint64_t out4[4]);
+/* The deferred tail of the schedule (0, 0, 0 when the program has none): when the schedule ends in a long run of narrow levels -- in
+ * the reference circuit the serial Poseidon sponges of the CEX commitments (src/witness/witness/witness.go:159-166 off-circuit,
+ * circuit/batch_create_user_circuit.go:129,320 in-circuit), ~170 000 levels of 1..13 instructions -- zkpor_groth16_prove_solve starts
+ * that run on a side stream as soon as its inputs are solved and overlaps it with the A, B and K multiplications, which see the
+ * run's wires as zero; their terms are added by small multiplications once the run is done (a multi-scalar multiplication is linear
+ * in the wire vector).  out3 = levels in the run, wires it solves, schedule step it starts before.  Env ZKPOR_DEFER_TAIL=0 disables
+ * the overlap, ZKPOR_TAIL_MIN sets the minimum run length (levels; default 2048). */
+int32_t zkpor_program_tail_info(zkpor_program *prog, uint64_t out3[3]);
+/* the ids of the wires the deferred run solves, ascending (cap >= the count zkpor_program_tail_info reports; host buffer) */
+int32_t zkpor_program_tail_wires(zkpor_program *prog, uint32_t *out_wires, uint64_t cap);
 /* r1cs.Solve: inputs = the n_public - 1 public then the n_secret secret values (Montgomery).  out_wires = n_wires elements,
  * out_a / out_b / out_c = n_constraints each (any of the four may be NULL).  pk supplies the commitment key and may be NULL for a
  * program without a commitment hint; out_commitment64 (may be NULL) receives the commitment point.  An unsatisfied constraint,

@@ -104,27 +104,76 @@ static void CV(batch_to_aff)(CV(aff) *out, const CV(jac) *in, size_t n) {
     free(pre);
 }
 
-/* Pippenger bucket method over plain (non-Montgomery) scalars; one (window, chunk) task at a time so the
- * caller can spread tasks over OpenMP threads.  Window w covers bits [w*c, w*c+c). */
-static void CV(msm_window_chunk)(CV(jac) *out, const CV(aff) *pts, const uint64_t *sc /* n x 4 */, size_t lo, size_t hi,
-                                 int w, int c) {
-    size_t nb = ((size_t)1 << c) - 1;
-    CV(jac) *bk = (CV(jac) *)malloc(sizeof(CV(jac)) * nb);
-    for (size_t i = 0; i < nb; i++) CV(jac_set_inf)(&bk[i]);
-    int bit = w * c;
-    for (size_t i = lo; i < hi; i++) {
-        const uint64_t *s = sc + 4 * i;
-        uint64_t d = 0;
-        int limb = bit >> 6, off = bit & 63;
-        if (limb < 4) {
-            d = s[limb] >> off;
-            if (off + c > 64 && limb + 1 < 4) d |= s[limb + 1] << (64 - off);
-            d &= nb;
-        }
-        if (d) CV(jac_add_mixed)(&bk[d - 1], &bk[d - 1], &pts[i]);
+/* Extended Jacobian coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; ZZ = 0: infinity) -- what gnark-crypto's MultiExp keeps its
+ * buckets in (g1JacExtended, ecc/bn254/g1.go, out of tree): a mixed addition is 8M + 2S (EFD "madd-2008-s"). */
+typedef struct { FT x, y, zz, zzz; } CV(xyzz);
+static inline void CV(xyzz_set_inf)(CV(xyzz) *p) { memset(p, 0, sizeof(*p)); }
+static inline int CV(xyzz_is_inf)(const CV(xyzz) *p) { return F_is_zero(&p->zz); }
+
+/* p += (neg ? -q : q), q affine */
+static inline void CV(xyzz_add_mixed)(CV(xyzz) *p, const CV(aff) *q, int neg) {
+    if (CV(aff_is_inf)(q)) return;
+    FT qy = q->y;
+    if (neg) F_neg(&qy, &qy);
+    if (CV(xyzz_is_inf)(p)) { p->x = q->x; p->y = qy; F_one(&p->zz); F_one(&p->zzz); return; }
+    FT U2, S2, Pp, Rr, PP, PPP, Q, t, X3;
+    F_mul(&U2, &q->x, &p->zz); F_mul(&S2, &qy, &p->zzz);
+    F_sub(&Pp, &U2, &p->x); F_sub(&Rr, &S2, &p->y);
+    if (F_is_zero(&Pp)) {
+        if (!F_is_zero(&Rr)) { CV(xyzz_set_inf)(p); return; }
+        /* doubling of the affine point ("mdbl-2008-s") */
+        FT U, V, W, S, M;
+        F_add(&U, &qy, &qy); F_sqr(&V, &U); F_mul(&W, &U, &V); F_mul(&S, &q->x, &V);
+        F_sqr(&M, &q->x); F_add(&t, &M, &M); F_add(&M, &M, &t);
+        F_sqr(&X3, &M); F_sub(&X3, &X3, &S); F_sub(&X3, &X3, &S);
+        F_sub(&t, &S, &X3); F_mul(&t, &M, &t); F_mul(&S, &W, &qy); F_sub(&p->y, &t, &S);
+        p->x = X3; p->zz = V; p->zzz = W;
+        return;
     }
-    CV(jac) run, sum; CV(jac_set_inf)(&run); CV(jac_set_inf)(&sum);
-    for (size_t i = nb; i-- > 0;) { CV(jac_add)(&run, &run, &bk[i]); CV(jac_add)(&sum, &sum, &run); }
+    F_sqr(&PP, &Pp); F_mul(&PPP, &Pp, &PP); F_mul(&Q, &p->x, &PP);
+    F_sqr(&X3, &Rr); F_sub(&X3, &X3, &PPP); F_sub(&X3, &X3, &Q); F_sub(&X3, &X3, &Q);
+    F_sub(&t, &Q, &X3); F_mul(&t, &Rr, &t); F_mul(&Q, &p->y, &PPP); F_sub(&p->y, &t, &Q);
+    p->x = X3;
+    F_mul(&p->zz, &p->zz, &PP); F_mul(&p->zzz, &p->zzz, &PPP);
+}
+/* the same point in Jacobian coordinates: Z = ZZZ, X' = X*ZZ^2, Y' = Y*ZZZ^2 */
+static inline void CV(xyzz_to_jac)(CV(jac) *r, const CV(xyzz) *p) {
+    if (CV(xyzz_is_inf)(p)) { CV(jac_set_inf)(r); return; }
+    FT t;
+    F_sqr(&t, &p->zz); F_mul(&r->x, &p->x, &t);
+    F_sqr(&t, &p->zzz); F_mul(&r->y, &p->y, &t);
+    r->z = p->zzz;
+}
+
+/* Pippenger bucket method with signed digits, as gnark-crypto's MultiExp does it (ecc/bn254/multiexp.go, out of tree: c-bit windows,
+ * digits in [-2^(c-1), 2^(c-1)), 2^(c-1) extended-Jacobian buckets per window, one running-sum reduction per window).  The digits come
+ * without a carry chain from s' = s + K, K = sum over all windows but the top one of 2^(c-1) * 2^(wc): digit_w = window_w(s') - 2^(c-1)
+ * (the top window is taken as it is; its value is small because s < 2^254).  One (window, chunk of points) task at a time so that the
+ * caller can spread tasks over OpenMP threads. */
+static inline uint64_t CV(window_of)(const uint64_t *s, int bit, int c) {
+    const int limb = bit >> 6, off = bit & 63;
+    if (limb >= 4) return 0;
+    uint64_t d = s[limb] >> off;
+    if (off + c > 64 && limb + 1 < 4) d |= s[limb + 1] << (64 - off);
+    return d & (((uint64_t)1 << c) - 1);
+}
+static void CV(msm_window_chunk)(CV(jac) *out, const CV(aff) *pts, const uint64_t *sc /* n x 4, already offset by K */, size_t lo, size_t hi,
+                                 int w, int c, int top) {
+    const size_t half = (size_t)1 << (c - 1), nb = half + 1;
+    CV(xyzz) *bk = (CV(xyzz) *)calloc(nb, sizeof(CV(xyzz)));
+    const int bit = w * c;
+    for (size_t i = lo; i < hi; i++) {
+        const int64_t raw = (int64_t)CV(window_of)(sc + 4 * i, bit, c);
+        const int64_t d = top ? raw : raw - (int64_t)half;
+        if (i + 8 < hi) __builtin_prefetch(&pts[i + 8]);
+        if (d > 0) CV(xyzz_add_mixed)(&bk[d - 1], &pts[i], 0);
+        else if (d < 0) CV(xyzz_add_mixed)(&bk[-d - 1], &pts[i], 1);
+    }
+    CV(jac) run, sum, b; CV(jac_set_inf)(&run); CV(jac_set_inf)(&sum);
+    for (size_t i = nb; i-- > 0;) {
+        if (!CV(xyzz_is_inf)(&bk[i])) { CV(xyzz_to_jac)(&b, &bk[i]); CV(jac_add)(&run, &run, &b); }
+        CV(jac_add)(&sum, &sum, &run);
+    }
     free(bk);
     *out = sum;
 }
@@ -132,10 +181,19 @@ static void CV(msm_window_chunk)(CV(jac) *out, const CV(aff) *pts, const uint64_
 static void CV(msm)(CV(jac) *out, const CV(aff) *pts, const uint64_t *sc /* plain */, size_t n, int threads) {
     if (n == 0) { CV(jac_set_inf)(out); return; }
     int c = 4;
-    { size_t t = n; int lg = 0; while (t >>= 1) lg++; c = lg <= 6 ? 3 : lg <= 10 ? 6 : lg <= 14 ? 10 : lg <= 18 ? 12 : lg <= 22 ? 14 : 16; }
-    int nw = (254 + c - 1) / c;
-    /* tasks = windows x point chunks: about three tasks per thread keep a dynamic schedule balanced (19 windows on 16 threads
-       with one chunk each would leave most threads idle for half of the time) */
+    { size_t t = n; int lg = 0; while (t >>= 1) lg++; c = lg <= 6 ? 3 : lg <= 10 ? 7 : lg <= 14 ? 11 : lg <= 18 ? 13 : lg <= 21 ? 15 : 16; }
+    const int nw = (255 + c - 1) / c;
+    /* s' = s + K */
+    uint64_t K[4] = {0, 0, 0, 0};
+    for (int w = 0; w < nw - 1; w++) { const int b = w * c + c - 1; K[b >> 6] |= (uint64_t)1 << (b & 63); }
+    uint64_t *sk = (uint64_t *)malloc(32 * n);
+    #pragma omp parallel for schedule(static) num_threads(threads)
+    for (size_t i = 0; i < n; i++) {
+        u128 cy = 0;
+        for (int j = 0; j < 4; j++) { cy += (u128)sc[4 * i + j] + K[j]; sk[4 * i + j] = (uint64_t)cy; cy >>= 64; }
+    }
+    /* tasks = windows x point chunks: about three tasks per thread keep a dynamic schedule balanced (16 windows on 16 threads
+       with one chunk each would leave most threads idle whenever one window is slower) */
     int chunks = 1;
     if (threads > 1 && n >= (1u << 14)) chunks = (3 * threads + nw - 1) / nw;
     size_t per = (n + chunks - 1) / chunks;
@@ -145,8 +203,9 @@ static void CV(msm)(CV(jac) *out, const CV(aff) *pts, const uint64_t *sc /* plai
     for (int t = 0; t < ntask; t++) {
         int w = t / chunks, ch = t % chunks;
         size_t lo = (size_t)ch * per, hi = lo + per; if (hi > n) hi = n; if (lo > hi) lo = hi;
-        CV(msm_window_chunk)(&part[t], pts, sc, lo, hi, w, c);
+        CV(msm_window_chunk)(&part[t], pts, sk, lo, hi, w, c, w == nw - 1);
     }
+    free(sk);
     CV(jac) acc; CV(jac_set_inf)(&acc);
     for (int w = nw - 1; w >= 0; w--) {
         for (int k = 0; k < c; k++) CV(jac_double)(&acc, &acc);

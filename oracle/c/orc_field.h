@@ -37,16 +37,28 @@ static inline void fe_sub_m(uint64_t *t, const uint64_t *m) {
 }
 
 static inline void fe_add(fe *z, const fe *x, const fe *y, const fparams *P) {
-    u128 c = 0; uint64_t t[4];
-    for (int i = 0; i < 4; i++) { c += (u128)x->l[i] + y->l[i]; t[i] = (uint64_t)c; c >>= 64; }
-    if (c || fe_geq_m(t, P->m)) fe_sub_m(t, P->m);
-    memcpy(z->l, t, 32);
+    /* both moduli are < 2^254: the sum fits four words; one branch-free conditional subtraction */
+    u128 c = (u128)x->l[0] + y->l[0]; const uint64_t t0 = (uint64_t)c;
+    c = (u128)x->l[1] + y->l[1] + (uint64_t)(c >> 64); const uint64_t t1 = (uint64_t)c;
+    c = (u128)x->l[2] + y->l[2] + (uint64_t)(c >> 64); const uint64_t t2 = (uint64_t)c;
+    c = (u128)x->l[3] + y->l[3] + (uint64_t)(c >> 64); const uint64_t t3 = (uint64_t)c;
+    u128 b = (u128)t0 - P->m[0]; const uint64_t r0 = (uint64_t)b;
+    b = (u128)t1 - P->m[1] - (uint64_t)((b >> 64) & 1); const uint64_t r1 = (uint64_t)b;
+    b = (u128)t2 - P->m[2] - (uint64_t)((b >> 64) & 1); const uint64_t r2 = (uint64_t)b;
+    b = (u128)t3 - P->m[3] - (uint64_t)((b >> 64) & 1); const uint64_t r3 = (uint64_t)b;
+    const int keep = (int)((b >> 64) & 1);
+    z->l[0] = keep ? t0 : r0; z->l[1] = keep ? t1 : r1; z->l[2] = keep ? t2 : r2; z->l[3] = keep ? t3 : r3;
 }
 static inline void fe_sub(fe *z, const fe *x, const fe *y, const fparams *P) {
-    u128 b = 0; uint64_t t[4];
-    for (int i = 0; i < 4; i++) { u128 d = (u128)x->l[i] - y->l[i] - (uint64_t)b; t[i] = (uint64_t)d; b = (d >> 64) & 1; }
-    if (b) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)t[i] + P->m[i]; t[i] = (uint64_t)c; c >>= 64; } }
-    memcpy(z->l, t, 32);
+    u128 b = (u128)x->l[0] - y->l[0]; const uint64_t t0 = (uint64_t)b;
+    b = (u128)x->l[1] - y->l[1] - (uint64_t)((b >> 64) & 1); const uint64_t t1 = (uint64_t)b;
+    b = (u128)x->l[2] - y->l[2] - (uint64_t)((b >> 64) & 1); const uint64_t t2 = (uint64_t)b;
+    b = (u128)x->l[3] - y->l[3] - (uint64_t)((b >> 64) & 1); const uint64_t t3 = (uint64_t)b;
+    const uint64_t mask = (uint64_t)0 - (uint64_t)((b >> 64) & 1);   /* borrow: add the modulus back */
+    u128 c = (u128)t0 + (P->m[0] & mask); z->l[0] = (uint64_t)c;
+    c = (u128)t1 + (P->m[1] & mask) + (uint64_t)(c >> 64); z->l[1] = (uint64_t)c;
+    c = (u128)t2 + (P->m[2] & mask) + (uint64_t)(c >> 64); z->l[2] = (uint64_t)c;
+    c = (u128)t3 + (P->m[3] & mask) + (uint64_t)(c >> 64); z->l[3] = (uint64_t)c;
 }
 static inline void fe_neg(fe *z, const fe *x, const fparams *P) {
     if (fe_is_zero(x)) { *z = *x; return; }
@@ -54,20 +66,32 @@ static inline void fe_neg(fe *z, const fe *x, const fparams *P) {
 }
 static inline void fe_dbl(fe *z, const fe *x, const fparams *P) { fe_add(z, x, x, P); }
 
-/* CIOS Montgomery product: z = x*y/R mod m */
+/* CIOS Montgomery product z = x*y/R mod m, fully unrolled, with gnark-crypto's "no-carry" shortcut (field/generator: valid when the top
+ * word of the modulus is < 2^63 - 1, as for both BN254 moduli): the two carry words of textbook CIOS collapse into t3 = C + A. */
 static inline void fe_mul(fe *z, const fe *x, const fe *y, const fparams *P) {
-    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    const uint64_t x0 = x->l[0], x1 = x->l[1], x2 = x->l[2], x3 = x->l[3];
+    const uint64_t q0 = P->m[0], q1 = P->m[1], q2 = P->m[2], q3 = P->m[3], inv = P->inv;
+    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#pragma GCC unroll 4
     for (int i = 0; i < 4; i++) {
-        u128 c = 0;
-        for (int j = 0; j < 4; j++) { c += (u128)x->l[j] * y->l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
-        c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
-        uint64_t q = t[0] * P->inv;
-        c = ((u128)q * P->m[0] + t[0]) >> 64;
-        for (int j = 1; j < 4; j++) { c += (u128)q * P->m[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
-        c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+        const uint64_t yi = y->l[i];
+        u128 a = (u128)x0 * yi + t0;
+        uint64_t A = (uint64_t)(a >> 64);
+        const uint64_t m = (uint64_t)a * inv;
+        u128 c = (u128)m * q0 + (uint64_t)a;
+        uint64_t C = (uint64_t)(c >> 64);
+        a = (u128)x1 * yi + t1 + A; A = (uint64_t)(a >> 64); c = (u128)m * q1 + (uint64_t)a + C; t0 = (uint64_t)c; C = (uint64_t)(c >> 64);
+        a = (u128)x2 * yi + t2 + A; A = (uint64_t)(a >> 64); c = (u128)m * q2 + (uint64_t)a + C; t1 = (uint64_t)c; C = (uint64_t)(c >> 64);
+        a = (u128)x3 * yi + t3 + A; A = (uint64_t)(a >> 64); c = (u128)m * q3 + (uint64_t)a + C; t2 = (uint64_t)c; C = (uint64_t)(c >> 64);
+        t3 = C + A;
     }
-    if (t[4] || fe_geq_m(t, P->m)) fe_sub_m(t, P->m);
-    memcpy(z->l, t, 32);
+    /* one conditional subtraction, branch-free */
+    u128 b = (u128)t0 - q0; const uint64_t r0 = (uint64_t)b;
+    b = (u128)t1 - q1 - (uint64_t)((b >> 64) & 1); const uint64_t r1 = (uint64_t)b;
+    b = (u128)t2 - q2 - (uint64_t)((b >> 64) & 1); const uint64_t r2 = (uint64_t)b;
+    b = (u128)t3 - q3 - (uint64_t)((b >> 64) & 1); const uint64_t r3 = (uint64_t)b;
+    const int keep = (int)((b >> 64) & 1);           /* borrow: t < q */
+    z->l[0] = keep ? t0 : r0; z->l[1] = keep ? t1 : r1; z->l[2] = keep ? t2 : r2; z->l[3] = keep ? t3 : r3;
 }
 static inline void fe_sqr(fe *z, const fe *x, const fparams *P) { fe_mul(z, x, x, P); }
 

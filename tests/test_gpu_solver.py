@@ -119,3 +119,36 @@ def test_solve_medium_wide_levels_vs_oracle(ctx):
     want, _ = orc.groth16_prove_program(inst["arr"], flat, inst["sc"]["infinity_a"], inst["sc"]["infinity_b"], inst["inputs_mont"], r, s)
     assert pk.prove_solve(prog, inst["inputs_mont"], r, s) == want
     prog.close(); pk.close()
+
+
+def test_deferred_tail_gives_the_same_proof(ctx, monkeypatch):
+    """The schedule's last run of narrow levels (the serial sponge of the CEX commitment) is started early on a side stream and its
+    wires are added to the A / B / K multiplications afterwards; the proof bytes must not change.  ZKPOR_TAIL_MIN forces the
+    deferral on a circuit whose tail is far shorter than the default threshold."""
+    inst = circuit_instance(seed=31, **dict(MEDIUM, users=40, chain_perms=12))
+    flat = inst["flat"]
+    r, s = 1234567, 7654321
+    want, _ = orc.groth16_prove_program(inst["arr"], flat, inst["sc"]["infinity_a"], inst["sc"]["infinity_b"], inst["inputs_mont"], r, s)
+    monkeypatch.setenv("ZKPOR_TAIL_MIN", "0")
+    plain = zk.Program(ctx, flat)
+    assert plain.stats()["deferred_tail"]["levels"] == 0
+    monkeypatch.setenv("ZKPOR_TAIL_MIN", "1")
+    prog = zk.Program(ctx, flat)
+    tail = prog.stats()["deferred_tail"]
+    assert tail["levels"] > 100 and tail["wires"] > 100 and tail["starts_before_step"] > 0
+    pk = make_pk(zk, ctx, inst)
+    assert pk.prove_solve(plain, inst["inputs_mont"], r, s) == want
+    for _ in range(3):                                   # the key's tail points are built on the first proof and reused
+        assert pk.prove_solve(prog, inst["inputs_mont"], r, s) == want
+    # the plain solve entry point runs the same program in place
+    w, a, b, c, _ = prog.solve(inst["inputs_mont"], pk)
+    ow, oa, ob, oc, _ = oracle_solution(inst)
+    assert np.array_equal(w, ow) and np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(c, oc)
+    # an unsatisfiable input still fails loudly (and leaves nothing running)
+    first, n_s, count, specs = [x for x in flat["secret_layout"] if any(k == "uint" for k, _ in x[3])][0]
+    j = [k for k, _ in specs].index("uint")
+    bad = list(inst["inputs"]); bad[first - 1 + j] = 1 << 70
+    with pytest.raises(zk.ZkporError, match="not satisfied|outside|division"):
+        pk.prove_solve(prog, orc.fr_mont(bad), r, s)
+    assert pk.prove_solve(prog, inst["inputs_mont"], r, s) == want
+    prog.close(); plain.close(); pk.close()

@@ -16,13 +16,14 @@ for st in $steps; do
     bench26cpu) timeout 1500 python bench.py > gpurun_out/s_bench26.json 2> gpurun_out/s_bench26.err; echo "bench26 rc=$?"; tail -c 2500 gpurun_out/s_bench26.json; tail -5 gpurun_out/s_bench26.err ;;
     ref26)   timeout 1700 python bench.py --impl reference > gpurun_out/s_ref26.json 2> gpurun_out/s_ref26.err; echo "ref26 rc=$?"; tail -c 1500 gpurun_out/s_ref26.json; tail -5 gpurun_out/s_ref26.err ;;
     ref24)   timeout 900 python bench.py --impl reference --log-n 24 > gpurun_out/s_ref24.json 2> gpurun_out/s_ref24.err; echo "ref24 rc=$?"; tail -c 1500 gpurun_out/s_ref24.json; tail -5 gpurun_out/s_ref24.err ;;
-    ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_bench22.csv python bench.py --log-n 22 --steps 1 --warmup 1 --no-cpu --no-e2e --no-parity > gpurun_out/s_ncu_l.log 2>&1; echo "ncu launches rc=$?" ;;
+    ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 30000 --csv --log-file gpurun_out/launches_bench22.csv python bench.py --log-n 22 --steps 1 --warmup 3 --no-cpu --no-e2e --no-parity > gpurun_out/s_ncu_l.log 2>&1; echo "ncu launches rc=$?" ;;
     solverbench22) timeout 600 python tools/solver_bench.py 22 > gpurun_out/s_solverbench22.log 2>&1; echo "solverbench22 rc=$?"; tail -8 gpurun_out/s_solverbench22.log | cut -c1-600 ;;
     solverbench26) timeout 900 python tools/solver_bench.py 26 96:512:9 96:512:0 > gpurun_out/s_solverbench26.log 2>&1; echo "solverbench26 rc=$?"; tail -4 gpurun_out/s_solverbench26.log | cut -c1-600 ;;
     sharded) timeout 600 python -m pytest tests/test_gpu_sharded.py -x -q > gpurun_out/s_sharded.log 2>&1; rc=$?; echo "sharded tests rc=$rc"; tail -25 gpurun_out/s_sharded.log
              [ $rc -ne 0 ] && exit $rc ;;
     bench22n) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NGPU --log-n 22 --no-cpu > gpurun_out/s_bench22_n$NGPU.json 2> gpurun_out/s_bench22_n$NGPU.err; echo "bench22n rc=$?"; tail -c 3000 gpurun_out/s_bench22_n$NGPU.json; tail -5 gpurun_out/s_bench22_n$NGPU.err ;;
     bench26n) timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NGPU --no-cpu --no-parity > gpurun_out/s_bench26_n$NGPU.json 2> gpurun_out/s_bench26_n$NGPU.err; echo "bench26n rc=$?"; tail -c 3000 gpurun_out/s_bench26_n$NGPU.json; tail -5 gpurun_out/s_bench26_n$NGPU.err ;;
+    solvertrace26) ZKPOR_SOLVE_TRACE=gpurun_out/solve_trace26.csv timeout 900 python tools/solver_bench.py 26 96:512:9 > gpurun_out/s_solvertrace26.log 2>&1; echo "solvertrace26 rc=$?"; tail -40 gpurun_out/s_solvertrace26.log | cut -c1-400 ;;
     ncu_narrow) timeout 900 ncu --set full --import-source on --clock-control none --kernel-id ::regex:k_solve_narrow:6 -f -o gpurun_out/r02_narrow python tools/solver_bench.py 22 96:512:9 > gpurun_out/s_ncu_narrow.log 2>&1; echo "ncu narrow rc=$?"; tail -3 gpurun_out/s_ncu_narrow.log | cut -c1-300 ;;
     *) echo "unknown step $st" ;;
   esac

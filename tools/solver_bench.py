@@ -15,6 +15,28 @@ import bench
 import zkpor_b200 as zk
 
 
+def summarise_trace(path):
+    """per-step device times of the last solve (csrc/solver.cu, ZKPOR_SOLVE_TRACE) by step type and width"""
+    import csv
+    rows = list(csv.DictReader(open(path)))
+    kinds = {0: "wide", 1: "narrow", 2: "count", 3: "commit"}
+    agg = {}
+    for r in rows:
+        k, cnt, ms = kinds[int(r["kind"])], int(r["count"]), float(r["ms"])
+        if k == "wide":
+            b = 1 << max(0, cnt.bit_length() - 1)
+            key = (k, b, int(r["has_div"]), int(int(r["n_long"]) > 0))
+        else:
+            key = (k, 0, 0, 0)
+        a = agg.setdefault(key, [0, 0.0, 0])
+        a[0] += 1; a[1] += ms; a[2] += cnt
+    print("kind  width>=  div long  steps     ms   us/step  instr")
+    for key in sorted(agg):
+        n, ms, cnt = agg[key]
+        print("%-6s %8d %3d %3d %7d %8.2f %8.2f %10d" % (key + (n, ms, 1e3 * ms / n, cnt)))
+    print("total ms", sum(a[1] for a in agg.values()), flush=True)
+
+
 def main():
     log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 22
     settings = sys.argv[2:] or ["96:512:9", "96:512:0", "96:512:17", "96:256:9", "24:512:9"]
@@ -50,6 +72,9 @@ def main():
         print(json.dumps(rec), flush=True)
         out.append(rec)
         prog.close()
+        tr = os.environ.get("ZKPOR_SOLVE_TRACE")
+        if tr and os.path.exists(tr):
+            summarise_trace(tr)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(dict(workload=wl.describe(), runs=out), open(os.path.join(ROOT, "gpurun_out", f"solver_bench_{log_n}.json"), "w"), indent=1)
 

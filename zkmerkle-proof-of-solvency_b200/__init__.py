@@ -197,8 +197,10 @@ class Context:
         _check(lib().zkpor_ctx_last_timings(self._h, buf, 16, C.byref(n)))
         return {lib().zkpor_stage_name(i).decode(): float(buf[i]) for i in range(n.value)}
 
-    def kernel_timing(self, enable: bool):
-        _check(lib().zkpor_ctx_kernel_timing(self._h, C.c_int32(1 if enable else 0)))
+    def kernel_timing(self, enable: bool, classes=None):
+        """classes: kernel class ids to time (None = all); an event pair per launch is not free"""
+        mask = 0 if classes is None else sum(1 << k for k in classes)
+        _check(lib().zkpor_ctx_kernel_timing(self._h, C.c_int32((1 | (mask << 8)) if enable else 0)))
 
     def kernel_stats(self, klass: int):
         ms, n, u = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
@@ -731,7 +733,16 @@ class Program:
     def stats(self) -> dict:
         out = (C.c_uint64 * 4)()
         _check(lib().zkpor_program_stats(self._h, out))
-        return dict(wide_levels=out[0], narrow_runs=out[1], narrow_levels=out[2], count_hints=out[3])
+        t = (C.c_uint64 * 3)()
+        _check(lib().zkpor_program_tail_info(self._h, t))
+        return dict(wide_levels=out[0], narrow_runs=out[1], narrow_levels=out[2], count_hints=out[3],
+                    deferred_tail=dict(levels=t[0], wires=t[1], starts_before_step=t[2]))
+
+    def tail_wires(self) -> np.ndarray:
+        n = self.stats()["deferred_tail"]["wires"]
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        _check(lib().zkpor_program_tail_wires(self._h, _ptr(out), C.c_uint64(out.size)))
+        return out[:n]
 
     def solve(self, inputs, pk: "ProvingKey" = None, want_abc=True):
         """r1cs.Solve: inputs = (n_public - 1 + n_secret, 4) uint64 Montgomery -> (wires, a, b, c, commitment) as numpy arrays"""

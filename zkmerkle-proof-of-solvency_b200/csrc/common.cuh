@@ -67,6 +67,9 @@ struct zkpor_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // H2D of a/b/c overlaps the wire-only MSMs of a proof
     cudaEvent_t copy_done = nullptr;
+    cudaStream_t tail_stream = nullptr;   // highest priority: the solver's deferred tail runs beside the multiplications (solver.cu)
+    // scalars whose bit is set read as zero in the NEXT msm_sort (bit i of the mask = scalar i; consumed by that call)
+    const uint32_t *scalar_mask = nullptr;
     int sm_count = 0;
     uint64_t launches = 0;
     int poseidon_out_lane = 1;
@@ -89,6 +92,7 @@ struct zkpor_ctx {
     float last_ms[zk::ST_COUNT];
     // per-launch kernel timers
     bool ktime_on = false;
+    uint32_t ktime_mask = 0xFFFFFFFFu;   // kernel classes that are timed while ktime_on
     std::vector<zk::KRec> klog;
     std::vector<cudaEvent_t> ev_free;
 };
@@ -130,7 +134,7 @@ inline cudaEvent_t kev_get(zkpor_ctx *ctx) {
 // brackets one launch of a timed kernel class: KTimed kt(ctx, KC_x, units); launch; kt.stop();
 struct KTimed {
     zkpor_ctx *ctx; KRec rec; bool on;
-    KTimed(zkpor_ctx *c, int klass, uint64_t units) : ctx(c), on(c->ktime_on) {
+    KTimed(zkpor_ctx *c, int klass, uint64_t units) : ctx(c), on(c->ktime_on && ((c->ktime_mask >> klass) & 1u)) {
         if (!on) return;
         rec.klass = klass; rec.units = units; rec.e0 = kev_get(c); rec.e1 = kev_get(c);
         cudaEventRecord(rec.e0, c->stream);

@@ -80,6 +80,7 @@ int32_t zkpor_ctx_create(int32_t device_id, zkpor_ctx **out) {
     ZK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ZK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     ZK_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); ZK_CUDA(cudaStreamCreateWithPriority(&ctx->tail_stream, cudaStreamNonBlocking, hi)); }
     for (int i = 0; i < ST_COUNT; i++) {
         ZK_CUDA(cudaEventCreate(&ctx->ev[i][0])); ZK_CUDA(cudaEventCreate(&ctx->ev[i][1]));
         ctx->ev_used[i] = false; ctx->last_ms[i] = 0.f;
@@ -96,6 +97,7 @@ int32_t zkpor_ctx_destroy(zkpor_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->tail_stream) cudaStreamSynchronize(ctx->tail_stream);
     zk::DevBuf *bufs[] = {&ctx->in_points, &ctx->in_scalars, &ctx->sort_idx, &ctx->sort_idx2, &ctx->view_cnt, &ctx->view_order, &ctx->part_buf, &ctx->part_meta, &ctx->bucket_cnt, &ctx->bucket_off, &ctx->bucket_cur,
                           &ctx->buckets, &ctx->partials, &ctx->windows, &ctx->misc, &ctx->ntt_a, &ctx->ntt_b, &ctx->ntt_c, &ctx->io, &ctx->heavy, &ctx->heavy_part, &ctx->order, &ctx->tree_a, &ctx->tree_b, &ctx->tree_meta, &ctx->dist_tmp};
     for (auto *b : bufs) b->release();
@@ -107,6 +109,7 @@ int32_t zkpor_ctx_destroy(zkpor_ctx *ctx) {
     for (int i = 0; i < ST_COUNT; i++) { cudaEventDestroy(ctx->ev[i][0]); cudaEventDestroy(ctx->ev[i][1]); }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->tail_stream) cudaStreamDestroy(ctx->tail_stream);
     cudaEventDestroy(ctx->copy_done);
     delete ctx;
     return ZKPOR_OK;
@@ -138,7 +141,8 @@ int32_t zkpor_ctx_kernel_timing(zkpor_ctx *ctx, int32_t enable) {
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     for (auto &r : ctx->klog) { ctx->ev_free.push_back(r.e0); ctx->ev_free.push_back(r.e1); }
     ctx->klog.clear();
-    ctx->ktime_on = enable != 0;
+    ctx->ktime_on = (enable & 1) != 0;
+    ctx->ktime_mask = (enable >> 8) ? (uint32_t)(enable >> 8) : 0xFFFFFFFFu;
     return ZKPOR_OK;
 }
 int32_t zkpor_ctx_kernel_stats(zkpor_ctx *ctx, int32_t klass, double *total_ms, uint64_t *launches, uint64_t *units) {

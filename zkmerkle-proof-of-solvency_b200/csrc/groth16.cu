@@ -14,6 +14,7 @@
 #include "internal.h"
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 using namespace ff;
 using namespace ec;
@@ -27,6 +28,15 @@ __global__ void k_gather_fr(const Fr *__restrict__ src, const uint32_t *__restri
     const uint4 *s = reinterpret_cast<const uint4 *>(src + idx[i]);
     uint4 *d = reinterpret_cast<uint4 *>(dst + i);
     d[0] = __ldg(s); d[1] = __ldg(s + 1);
+}
+
+template <class P>
+__global__ void k_gather_points(const P *__restrict__ src, const uint32_t *__restrict__ idx, uint64_t n, P *__restrict__ dst) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr uint32_t Q = sizeof(P) / 16;
+    if (t >= n * Q) return;
+    const uint64_t i = t / Q; const uint32_t q = (uint32_t)(t % Q);
+    reinterpret_cast<uint4 *>(dst + i)[q] = __ldg(reinterpret_cast<const uint4 *>(src + idx[i]) + q);
 }
 
 static int32_t upload(void **dst, const void *src, size_t bytes) {
@@ -103,6 +113,93 @@ static int32_t combine_commit(zkpor_ctx *ctx, zkpor_pk *pk, G1XYZZ *commit, G1XY
     return ZKPOR_OK;
 }
 
+static void tail_key_free(zkpor_pk *pk) {
+    zkpor_pk::TailKey &t = pk->tail;
+    for (void *q : {(void *)t.w_a, (void *)t.w_b, (void *)t.w_k, (void *)t.A, (void *)t.B1, (void *)t.K, (void *)t.B2}) if (q) cudaFree(q);
+    t = zkpor_pk::TailKey();
+}
+
+// The A / B / K key points of the wires a program's deferred tail solves (within this key's wire range), as compact arrays: the tail's
+// contribution to the three wire multiplications is a small multiplication of its own once the tail has finished (Sum s_i P_i is
+// linear in the wire vector).  Built on the first proof of a (key, program) pair.
+static int32_t tail_key_build(zkpor_ctx *ctx, zkpor_pk *pk, const SolverTail &tail) {
+    if (pk->tail.prog_uid == tail.uid) return ZKPOR_OK;
+    tail_key_free(pk);
+    const uint64_t words = (pk->n_wires + 31) / 32;
+    std::vector<uint2> maps[3];
+    const uint2 *dmap[3] = {pk->map_a, pk->map_b, pk->map_k};
+    for (int k = 0; k < 3; k++) { maps[k].resize(words); if (words) ZK_CUDA(cudaMemcpy(maps[k].data(), dmap[k], words * sizeof(uint2), cudaMemcpyDeviceToHost)); }
+    std::vector<uint32_t> wid[3], pid[3];
+    for (uint32_t wire : *tail.wires) {
+        if (wire < pk->wire_first || wire >= pk->wire_first + pk->n_wires) continue;
+        const uint64_t j = wire - pk->wire_first; const uint32_t bit = (uint32_t)(j & 31);
+        for (int k = 0; k < 3; k++) {
+            const uint2 m = maps[k][j >> 5];
+            if ((m.x >> bit) & 1u) continue;
+            wid[k].push_back(wire); pid[k].push_back(m.y + (uint32_t)__builtin_popcount(~m.x & ((1u << bit) - 1u)));
+        }
+    }
+    zkpor_pk::TailKey &t = pk->tail;
+    t.n_a = wid[0].size(); t.n_b = wid[1].size(); t.n_k = wid[2].size();
+    uint32_t **wdst[3] = {&t.w_a, &t.w_b, &t.w_k};
+    for (int k = 0; k < 3; k++) {
+        const uint64_t n = wid[k].size();
+        if (n == 0) continue;
+        ZK_TRY(upload((void **)wdst[k], wid[k].data(), n * 4));
+        uint32_t *d_pid = nullptr;
+        ZK_TRY(upload((void **)&d_pid, pid[k].data(), n * 4));
+        int32_t rc = ZKPOR_OK;
+        auto gather = [&](auto **dst, const auto *src) {
+            using P = std::remove_pointer_t<std::remove_pointer_t<decltype(dst)>>;
+            if (cudaMalloc((void **)dst, n * sizeof(P)) != cudaSuccess) { set_error("prove: out of device memory for the tail's key points"); rc = ZKPOR_ERR_OOM; return; }
+            k_gather_points<P><<<grid_for(n * (sizeof(P) / 16), 256), 256, 0, ctx->stream>>>(src, d_pid, n, *dst);
+        };
+        if (k == 0) gather(&t.A, pk->A);
+        if (k == 1) { gather(&t.B1, pk->B1); if (rc == ZKPOR_OK) gather(&t.B2, pk->B2); }
+        if (k == 2) gather(&t.K, pk->K);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_pid);
+        ZK_TRY(rc);
+    }
+    t.prog_uid = tail.uid;
+    return ZKPOR_OK;
+}
+
+// adds the tail wires' terms to Ar, Bs1, Bs2 and Krs-K (the shared sort saw those wires as zero)
+static int32_t tail_delta(zkpor_ctx *ctx, zkpor_pk *pk, const Fr *dw, ProofParts &pp) {
+    const zkpor_pk::TailKey &t = pk->tail;
+    ZK_TRY(pk->sub.reserve(std::max({t.n_a, t.n_b, t.n_k, pk->n_ck, (uint64_t)1}) * 32));
+    Fr *sub = pk->sub.as<Fr>();
+    MsmSorted srt;
+    if (t.n_a) {
+        G1XYZZ r;
+        ZK_LAUNCH(ctx, k_gather_fr, grid_for(t.n_a, 256), 256, 0, dw, (const uint32_t *)t.w_a, t.n_a, sub);
+        ZK_TRY(msm_g1_dev(ctx, t.A, sub, t.n_a, ZKPOR_SCALARS_MONT, &r));
+        pp.ar.add(r);
+    }
+    if (t.n_b) {
+        G1XYZZ r; G2XYZZ r2;
+        ZK_LAUNCH(ctx, k_gather_fr, grid_for(t.n_b, 256), 256, 0, dw, (const uint32_t *)t.w_b, t.n_b, sub);
+        ZK_TRY(msm_sort(ctx, sub, t.n_b, ZKPOR_SCALARS_MONT, &srt));
+        ZK_TRY(msm_accumulate_g1(ctx, t.B1, srt, &r));
+        ZK_TRY(msm_accumulate_g2(ctx, t.B2, srt, &r2));
+        pp.bs1.add(r); pp.bs2.add(r2);
+    }
+    if (t.n_k) {
+        G1XYZZ r;
+        ZK_LAUNCH(ctx, k_gather_fr, grid_for(t.n_k, 256), 256, 0, dw, (const uint32_t *)t.w_k, t.n_k, sub);
+        ZK_TRY(msm_g1_dev(ctx, t.K, sub, t.n_k, ZKPOR_SCALARS_MONT, &r));
+        pp.krs_k.add(r);
+    }
+    return ZKPOR_OK;
+}
+
+// ZKPOR_DEFER_TAIL=0: the solver's tail runs in place (measurement knob; the proof is the same)
+static bool defer_tail_enabled() {
+    static const bool on = [] { const char *v = getenv("ZKPOR_DEFER_TAIL"); return v == nullptr || atoi(v) != 0; }();
+    return on;
+}
+
 }  // namespace zk
 
 using namespace zk;
@@ -114,6 +211,7 @@ int32_t zkpor_pk_free(zkpor_ctx *ctx, zkpor_pk *pk) {
     if (!pk) return ZKPOR_OK;
     void *ptrs[] = {pk->A, pk->B1, pk->K, pk->Z, pk->ck, pk->ck_sigma, pk->B2, pk->idx_c, pk->map_a, pk->map_b, pk->map_k};
     for (void *p : ptrs) if (p) cudaFree(p);
+    tail_key_free(pk);
     pk->wires.release(); pk->sub.release();
     delete pk;
     return ZKPOR_OK;
@@ -258,7 +356,8 @@ static int32_t prove_body(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_pr
     const void *dw;
     ProofParts pp;
     pp.commit = G1XYZZ::inf(); pp.pok = G1XYZZ::inf();
-    bool commit_done = false;
+    bool commit_done = false, deferred = false;
+    SolverTail tail{};
     if (prog != nullptr) {
         // r1cs.Solve on the device: inputs -> wires[1 ..], every other wire by the level schedule; the commitment hint leaves the
         // commitment and its proof of knowledge behind.  Sharded: every rank solves the whole system (the schedule is a latency
@@ -271,7 +370,10 @@ static int32_t prove_body(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_pr
         ZK_CUDA(cudaMemcpyAsync(w + 1, wires, program_inputs(prog) * 32, cudaMemcpyDefault, ctx->stream));
         stage_end(ctx, ST_H2D);
         stage_begin(ctx, ST_SOLVE);
-        ZK_TRY(solver_run(ctx, prog, pk, w, &pp.commit, &pp.pok, &commit_done));
+        deferred = defer_tail_enabled() && solver_tail_info(prog, &tail);
+        if (deferred) ZK_TRY(tail_key_build(ctx, pk, tail));
+        ZK_TRY(solver_run(ctx, prog, pk, w, &pp.commit, &pp.pok, &commit_done, deferred));
+        if (deferred) stage_end(ctx, ST_SOLVE);   // the head of the schedule; the tail runs beside the multiplications below
         dw = w;
     } else {
         stage_begin(ctx, ST_H2D);
@@ -283,25 +385,32 @@ static int32_t prove_body(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_pr
     const void *src[3] = {a, b, c};
     Fr *dst[3] = {ctx->ntt_a.as<Fr>(), ctx->ntt_b.as<Fr>(), ctx->ntt_c.as<Fr>()};
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));   // the previous call's use of the NTT buffers is over
-    if (world > 1) {
-        // this rank's rows rank, rank + world, ... of a, b, c: the cyclic split the sharded transform starts from
-        ZK_TRY(ctx->dist_tmp.reserve(bytes));
-        ZK_TRY(r1cs_eval_strided_dev(ctx, cs, (const Fr *)dw, dst[0], dst[1], dst[2], (uint64_t)rank, (uint64_t)world, m));
-        int32_t ok_all[8], ok_mine = prog != nullptr ? r1cs_check_dev(ctx, dst[0], dst[1], dst[2], m) : ZKPOR_OK;
-        if (prog != nullptr) {
-            ZK_TRY(comm_all_gather_host(ctx, &ok_mine, ok_all, sizeof ok_mine));
-            for (int j = 0; j < world; j++)
-                if (ok_all[j] != ZKPOR_OK) { if (ok_mine == ZKPOR_OK) set_error("solve: a constraint is not satisfied (found by rank %d)", j); return ok_all[j]; }
-            stage_end(ctx, ST_SOLVE);
+    // a = L w, b = R w, c = O w on the device (and, after a solve, gnark's satisfaction check): needs every wire, so with a deferred
+    // tail it runs after the wire multiplications instead of ahead of them
+    auto eval_abc = [&]() -> int32_t {
+        if (world > 1) {
+            // this rank's rows rank, rank + world, ... of a, b, c: the cyclic split the sharded transform starts from
+            ZK_TRY(r1cs_eval_strided_dev(ctx, cs, (const Fr *)dw, dst[0], dst[1], dst[2], (uint64_t)rank, (uint64_t)world, m));
+            int32_t ok_all[8], ok_mine = prog != nullptr ? r1cs_check_dev(ctx, dst[0], dst[1], dst[2], m) : ZKPOR_OK;
+            if (prog != nullptr) {
+                ZK_TRY(comm_all_gather_host(ctx, &ok_mine, ok_all, sizeof ok_mine));
+                for (int j = 0; j < world; j++)
+                    if (ok_all[j] != ZKPOR_OK) { if (ok_mine == ZKPOR_OK) set_error("solve: a constraint is not satisfied (found by rank %d)", j); return ok_all[j]; }
+                if (!deferred) stage_end(ctx, ST_SOLVE);
+            }
+            return ZKPOR_OK;
         }
-    } else if (cs != nullptr) {
-        // constraint evaluation on the device: needs only the wires, runs ahead of the multiplications on the compute stream
         for (int k = 0; k < 3; k++) if (bytes > in_bytes) ZK_CUDA(cudaMemsetAsync((uint8_t *)dst[k] + in_bytes, 0, bytes - in_bytes, ctx->stream));
         ZK_TRY(r1cs_eval_dev(ctx, cs, (const Fr *)dw, dst[0], dst[1], dst[2]));
         if (prog != nullptr) {   // gnark's Solve fails on the first unsatisfied constraint; here one pass over a, b, c
             ZK_TRY(r1cs_check_dev(ctx, dst[0], dst[1], dst[2], n_constraints));
-            stage_end(ctx, ST_SOLVE);
+            if (!deferred) stage_end(ctx, ST_SOLVE);
         }
+        return ZKPOR_OK;
+    };
+    if (world > 1) ZK_TRY(ctx->dist_tmp.reserve(bytes));
+    if (cs != nullptr) {
+        if (!deferred) ZK_TRY(eval_abc());
     } else {
         for (int k = 0; k < 3; k++) {
             ZK_CUDA(cudaMemcpyAsync(dst[k], src[k], in_bytes, cudaMemcpyDefault, ctx->copy_stream));
@@ -311,7 +420,7 @@ static int32_t prove_body(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_pr
     // computeH runs on the copy stream, right behind the transfers of a, b, c, concurrently with the wire-side sorts and
     // multiplications of the compute stream: the counting sorts are bound by L2 atomics and scattered stores and leave the
     // integer pipe idle, which the NTT butterflies fill.  The Z multiplication waits for h (copy_done).
-    const bool overlap = overlap_ntt() && world == 1;
+    const bool overlap = overlap_ntt() && world == 1 && !deferred;
     if (overlap) {
         if (cs != nullptr) {   // a, b, c were produced on the compute stream
             ZK_CUDA(cudaEventRecord(ctx->copy_done, ctx->stream));
@@ -331,6 +440,7 @@ static int32_t prove_body(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_pr
     // one digit extraction + counting sort over (this rank's range of) the wire vector, four accumulations through their wire maps
     const Fr *dw_mine = (const Fr *)dw + pk->wire_first;
     if (pk->n_wires) {
+        if (deferred) ctx->scalar_mask = tail.mask + pk->wire_first / 32;   // wire ranges start at multiples of 32
         ZK_TRY(msm_sort(ctx, dw_mine, pk->n_wires, ZKPOR_SCALARS_MONT, &srt));
         MsmSorted view;
         if (pk->n_a) {
@@ -346,6 +456,11 @@ static int32_t prove_body(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_pr
             ZK_TRY(msm_view(ctx, srt, pk->map_k, &view));
             ZK_TRY(msm_accumulate_g1(ctx, pk->K, view, &pp.krs_k, pk->n_k));
         }
+    }
+    if (deferred) {
+        ZK_TRY(solver_tail_join(ctx, prog));
+        ZK_TRY(tail_delta(ctx, pk, (const Fr *)dw, pp));
+        ZK_TRY(eval_abc());
     }
     ZK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
     if (world > 1) ZK_TRY(compute_h_dist(ctx, dst[0], dst[1], dst[2], ctx->dist_tmp.as<Fr>(), pk->log_n));
@@ -367,7 +482,7 @@ static int32_t prove_body(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_pr
 static int32_t prove_impl(zkpor_ctx *ctx, zkpor_pk *pk, zkpor_r1cs *cs, zkpor_program *prog, const void *wires, const void *a, const void *b,
                           const void *c, uint64_t n_constraints, const uint8_t r_be[32], const uint8_t s_be[32], uint8_t *out_proof, uint32_t *out_len) {
     const int32_t rc = prove_body(ctx, pk, cs, prog, wires, a, b, c, n_constraints, r_be, s_be, out_proof, out_len);
-    if (rc != ZKPOR_OK) comm_abort(ctx);
+    if (rc != ZKPOR_OK) { comm_abort(ctx); ctx->scalar_mask = nullptr; if (prog) solver_tail_abandon(ctx, prog); }
     return rc;
 }
 

@@ -30,6 +30,10 @@ struct zkpor_pk {
     int shard_rank = 0, shard_world = 1;
     uint64_t wire_first = 0, n_wires_total = 0, z_first = 0;
     zk::DevBuf wires, sub;
+    // key points of the wires a program's deferred tail solves (groth16.cu, built on first use per program): compact copies of the
+    // A / B / K entries of those wires and the wire ids to gather their values from
+    struct TailKey { uint64_t prog_uid = 0, n_a = 0, n_b = 0, n_k = 0; uint32_t *w_a = nullptr, *w_b = nullptr, *w_k = nullptr;
+                     ec::G1Affine *A = nullptr, *B1 = nullptr, *K = nullptr; ec::G2Affine *B2 = nullptr; } tail;
 };
 
 namespace zk {
@@ -87,7 +91,12 @@ ff::Fr commitment_challenge_g1(const ec::G1Affine &commitment);
 
 // witness solver (solver.cu): wires[0] = 1, wires[1 ..] = inputs on entry; every other wire is written.  commit / pok receive the
 // commitment hint's by-products when the program has one (has_commit).
-int32_t solver_run(zkpor_ctx *ctx, zkpor_program *prog, zkpor_pk *pk, ff::Fr *d_wires, ec::G1XYZZ *commit, ec::G1XYZZ *pok, bool *has_commit);
+// defer_tail: see run_schedule in solver.cu -- the caller must solver_tail_join before it reads the tail's wires
+int32_t solver_run(zkpor_ctx *ctx, zkpor_program *prog, zkpor_pk *pk, ff::Fr *d_wires, ec::G1XYZZ *commit, ec::G1XYZZ *pok, bool *has_commit, bool defer_tail);
+struct SolverTail { uint64_t uid; const uint32_t *mask; const std::vector<uint32_t> *wires; uint64_t levels; };   // mask: device bitmask over all wires; wires: ascending ids (host)
+bool solver_tail_info(const zkpor_program *prog, SolverTail *out);
+int32_t solver_tail_join(zkpor_ctx *ctx, zkpor_program *prog);
+void solver_tail_abandon(zkpor_ctx *ctx, zkpor_program *prog);
 zkpor_r1cs *program_matrices(zkpor_program *prog);
 uint64_t program_inputs(const zkpor_program *prog);
 // a[k]*b[k] == c[k] for every constraint row; ZKPOR_ERR_STATE naming the first violated row otherwise

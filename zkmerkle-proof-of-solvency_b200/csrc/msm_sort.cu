@@ -22,9 +22,13 @@ MsmPlan msm_plan(uint64_t n) {
 }
 
 // ------------------------------------------------------------------------------------------------ scalar side
-__global__ void k_from_mont(const Fr *__restrict__ in, Fr *__restrict__ out, uint64_t n) {
+// mask (optional): scalars whose bit is set are not read and count as zero -- wires that a concurrent kernel is still solving
+// (the solver's deferred tail); their terms are added by a multiplication of their own afterwards
+__global__ void k_from_mont(const Fr *__restrict__ in, Fr *__restrict__ out, uint64_t n, const uint32_t *__restrict__ mask) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = Fr::from_mont(in[i]);
+    if (i >= n) return;
+    if (mask != nullptr && ((mask[i >> 5] >> (i & 31)) & 1u)) { out[i] = Fr::zero(); return; }
+    out[i] = Fr::from_mont(in[i]);
 }
 
 // plain scalars may be any 256-bit integers: bring them below r (at most five subtractions), so that the signed-digit recoding's
@@ -374,7 +378,10 @@ int32_t msm_sort(zkpor_ctx *ctx, const void *d_scalars, uint64_t n, uint32_t fla
     stage_begin(ctx, ST_DIGITS);
     const uint32_t *plain = (const uint32_t *)d_scalars;
     ZK_TRY(ctx->misc.reserve(n * 32));
-    if (!(flags & ZKPOR_SCALARS_PLAIN)) ZK_LAUNCH(ctx, k_from_mont, grid_for(n, 256), 256, 0, (const Fr *)d_scalars, ctx->misc.as<Fr>(), n);
+    const uint32_t *mask = ctx->scalar_mask;
+    ctx->scalar_mask = nullptr;
+    ZK_REQUIRE(mask == nullptr || !(flags & ZKPOR_SCALARS_PLAIN), "msm_sort: a scalar mask needs Montgomery scalars");
+    if (!(flags & ZKPOR_SCALARS_PLAIN)) ZK_LAUNCH(ctx, k_from_mont, grid_for(n, 256), 256, 0, (const Fr *)d_scalars, ctx->misc.as<Fr>(), n, mask);
     else ZK_LAUNCH(ctx, k_canon_plain, grid_for(n, 256), 256, 0, (const Fr *)d_scalars, ctx->misc.as<Fr>(), n);
     plain = ctx->misc.as<uint32_t>();
     ZK_CUDA(cudaMemsetAsync(ctx->bucket_cnt.p, 0, slots * 4, ctx->stream));

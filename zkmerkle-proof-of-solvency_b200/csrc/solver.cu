@@ -47,6 +47,7 @@ struct ProgView {
     Fr *w; uint8_t *solved; unsigned long long *err;      // err: (code << 56) | row or hint id, first writer wins
     struct Pending *pend;                                 // wide levels: divisions deferred to k_solve_div, slot = position in the level
     uint8_t *step_div;                                    // dry run: step s has at least one division
+    uint32_t *wstep; uint32_t cur_step;                   // dry run: wstep[wire] = 1 + the schedule step that solves it (0: an input)
 };
 // w[wire] = num / den, written by the evaluating group, consumed (and cleared) by k_solve_div
 struct alignas(16) Pending { Fr num, den; uint32_t wire, state, pad0, pad1; };   // state: 0 empty, 1 division, 2 division where den = 0 gives 0 (InvZero)
@@ -73,6 +74,13 @@ struct zkpor_program {
     bool has_commit = false;
     uint32_t narrow_max = zk::NARROW_MAX; int narrow_threads = zk::NARROW_THREADS; uint32_t long_row = 0;
     zk::DevBuf wires, abc;
+    // The deferred tail (see run_schedule): the last step, when it is a long run of narrow levels, starts on a side stream as soon as
+    // the steps it reads from have been enqueued (tail_after) and runs beside the rest of the proof; its wires are listed here.
+    int64_t tail_step = -1; uint64_t tail_after = 0, n_tail_wires = 0, uid = 0;
+    uint32_t *tail_wires = nullptr, *tail_mask = nullptr; uint32_t *wstep = nullptr;
+    std::vector<uint32_t> h_tail_wires;
+    cudaEvent_t tail_go = nullptr, tail_done = nullptr; bool tail_running = false;
+    const char *trace_path = nullptr;              // env ZKPOR_SOLVE_TRACE: per-step device times of the next solve, written as CSV
 };
 
 namespace zk {
@@ -161,7 +169,7 @@ template <bool DRY>
 __device__ void exec_hint(const ProgView &v, uint32_t h, uint64_t slot, uint64_t step) {
     const uint32_t fn = v.hint_fn[h], param = v.hint_param[h], out = v.hint_out[h], n_out = v.hint_nout[h];
     if (DRY) {
-        for (uint32_t k = 0; k < n_out; k++) v.solved[out + k] = 1;
+        for (uint32_t k = 0; k < n_out; k++) { v.solved[out + k] = 1; v.wstep[out + k] = v.cur_step + 1; }
         if (fn == ZKPOR_HINT_INVZERO && step != NO_SLOT) v.step_div[step] = 1;
         return;
     }
@@ -264,7 +272,7 @@ __device__ __forceinline__ void exec_instr(const ProgView &v, uint32_t packed, i
         if (total == 0) { if (lane == 0) v.solve_e[row] = SOLVE_NONE; return; }
         if (found) {
             const int side = (int)(cand >> 62); const uint64_t pos = cand & ((1ull << 62) - 1);
-            v.solve_e[row] = cand; v.solved[v.wire[side][pos]] = 1;
+            v.solve_e[row] = cand; v.solved[v.wire[side][pos]] = 1; v.wstep[v.wire[side][pos]] = v.cur_step + 1;
             const uint32_t cid = v.coef[side][pos];
             if (step != NO_SLOT && (side != 2 || (cid != v.one_id && cid != v.minus_one_id))) v.step_div[step] = 1;
         }
@@ -433,9 +441,40 @@ __global__ void k_count_store(ProgView v, const uint32_t *cnt, uint32_t out, uin
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n_out) v.w[out + k] = Fr::from_u64(cnt[k]);
 }
-__global__ void k_mark_solved(uint8_t *solved, uint64_t first, uint64_t n) {
+__global__ void k_mark_solved(uint8_t *solved, uint32_t *wstep, uint32_t step, uint64_t first, uint64_t n) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) solved[first + k] = 1;
+    if (k < n) { solved[first + k] = 1; wstep[first + k] = step + 1; }
+}
+
+// Upload-time analysis of the deferred tail, one thread per schedule entry of the step: which wires does the step solve (appended to
+// out_wires when given; *cursor counts them), and which is the latest earlier step it reads from (dep = max of wstep over its reads).
+__global__ void k_tail_scan(ProgView v, uint64_t p0, uint64_t p1, uint32_t tail_mark, uint32_t *out_wires, unsigned long long *cursor, uint32_t *dep) {
+    const uint64_t p = p0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    const uint32_t packed = v.sched[p];
+    uint32_t d = 0;
+    auto reads = [&](uint32_t wire) { const uint32_t ws = v.wstep[wire]; if (ws != tail_mark && ws > d) d = ws; };
+    auto aux_rows = [&](uint64_t r0, uint64_t r1) { for (uint64_t e = v.aux_ptr[r0], e1 = v.aux_ptr[r1]; e < e1; e++) reads(v.aux_wire[e]); };
+    if (packed & HINT_BIT) {
+        const uint32_t h = packed & ~HINT_BIT, n_out = v.hint_nout[h], out = v.hint_out[h];
+        aux_rows(v.hint_in0[h], v.hint_in1[h]);
+        if (v.hint_fn[h] == ZKPOR_HINT_LOOKUP) aux_rows(v.table_ptr[v.hint_param[h]], v.table_ptr[v.hint_param[h] + 1]);
+        const unsigned long long at = atomicAdd(cursor, (unsigned long long)n_out);
+        if (out_wires) for (uint32_t k = 0; k < n_out; k++) out_wires[at + k] = out + k;
+    } else {
+        for (int side = 0; side < 3; side++)
+            for (uint64_t e = v.ptr[side][packed], e1 = v.ptr[side][(uint64_t)packed + 1]; e < e1; e++) reads(v.wire[side][e]);
+        const uint64_t se = v.solve_e[packed];
+        if (se != SOLVE_NONE) {
+            const unsigned long long at = atomicAdd(cursor, 1ull);
+            if (out_wires) out_wires[at] = v.wire[(int)(se >> 62)][se & ((1ull << 62) - 1)];
+        }
+    }
+    if (d) atomicMax(dep, d);
+}
+__global__ void k_wire_mask(const uint32_t *__restrict__ wires, uint64_t n, uint32_t *mask) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicOr(mask + (wires[i] >> 5), 1u << (wires[i] & 31));
 }
 
 __global__ void k_check_abc(const Fr *__restrict__ a, const Fr *__restrict__ b, const Fr *__restrict__ c, uint64_t n, unsigned long long *first_bad) {
@@ -464,7 +503,7 @@ static ProgView make_view(zkpor_program *p, Fr *w, uint8_t *solved) {
     v.sched = p->sched; v.lvl_start = p->lvl_start;
     v.hint_fn = p->hint_fn; v.hint_param = p->hint_param; v.hint_out = p->hint_out; v.hint_nout = p->hint_nout; v.hint_in0 = p->hint_in0; v.hint_in1 = p->hint_in1;
     v.table_ptr = p->table_ptr; v.solve_e = p->solve_e; v.w = w; v.solved = solved; v.err = p->err;
-    v.pend = p->pend; v.step_div = p->step_div;
+    v.pend = p->pend; v.step_div = p->step_div; v.wstep = p->wstep; v.cur_step = 0;
     return v;
 }
 
@@ -481,12 +520,40 @@ static int32_t solve_error(zkpor_program *p, zkpor_ctx *ctx, const char *what) {
 }
 
 // runs the schedule: DRY = find every R1C instruction's unknown on solved-flags, else solve
+// defer_tail (proofs only): the program's tail step -- a long run of narrow levels at the end of the schedule: in the reference circuit
+// the serial sponge of the CEX commitment, ~170 000 levels of one to thirteen instructions, 70 % of the solve on one SM -- is launched
+// on the context's high-priority side stream as soon as the steps it reads from are enqueued, and the caller goes on with everything
+// that is linear in the wire vector (the A, B, K multiplications, with the tail's wires masked to zero) before solver_tail_join.
 template <bool DRY>
-static int32_t run_schedule(zkpor_ctx *ctx, zkpor_program *p, zkpor_pk *pk, Fr *w, uint8_t *solved, G1XYZZ *commit, G1XYZZ *pok) {
+static int32_t run_schedule(zkpor_ctx *ctx, zkpor_program *p, zkpor_pk *pk, Fr *w, uint8_t *solved, G1XYZZ *commit, G1XYZZ *pok, bool defer_tail = false) {
     ProgView v = make_view(p, w, solved);
     ZK_CUDA(cudaMemsetAsync(p->err, 0, 8, ctx->stream));
+    const bool trace = !DRY && p->trace_path != nullptr;
+    std::vector<cudaEvent_t> tev;
+    if (trace) { tev.resize(p->steps.size() + 1); for (auto &e : tev) cudaEventCreate(&e); }
+    defer_tail = defer_tail && !DRY && p->tail_step >= 0;
     for (size_t si = 0; si < p->steps.size(); si++) {
         const Step &s = p->steps[si];
+        if (trace) cudaEventRecord(tev[si], ctx->stream);
+        v.cur_step = (uint32_t)si;
+        if (defer_tail && si == p->tail_after) {
+            const Step &t = p->steps[(size_t)p->tail_step];
+            ZK_CUDA(cudaEventRecord(p->tail_go, ctx->stream));
+            ZK_CUDA(cudaStreamWaitEvent(ctx->tail_stream, p->tail_go, 0));
+            cudaStream_t main_stream = ctx->stream;
+            ctx->stream = ctx->tail_stream;
+            int32_t rc = ZKPOR_OK;
+            { KTimed kt(ctx, KC_SOLVE_NARROW, t.b - t.a);
+              k_solve_narrow<false><<<1, p->narrow_threads, 0, ctx->stream>>>(v, t.a, t.b);
+              ctx->launches++;
+              if (cudaGetLastError() != cudaSuccess) { set_error("solve: launch of the deferred tail failed"); rc = ZKPOR_ERR_CUDA; }
+              kt.stop(); }
+            cudaEventRecord(p->tail_done, ctx->stream);
+            ctx->stream = main_stream;
+            ZK_TRY(rc);
+            p->tail_running = true;
+        }
+        if (defer_tail && (int64_t)si == p->tail_step) continue;
         switch (s.kind) {
         case STEP_WIDE: {
             const uint64_t count = s.b - s.a, blocks = (s.n_long + 7) / 8 + (((count - s.n_long) * WIDE_GS + 255) / 256);
@@ -504,7 +571,7 @@ static int32_t run_schedule(zkpor_ctx *ctx, zkpor_program *p, zkpor_pk *pk, Fr *
         }
         case STEP_COUNT: {
             const uint32_t h = (uint32_t)s.a, n_out = p->h_hint_nout[h], out = p->h_hint_out[h];
-            if (DRY) { ZK_LAUNCH(ctx, k_mark_solved, grid_for(n_out, 256), 256, 0, solved, (uint64_t)out, (uint64_t)n_out); break; }
+            if (DRY) { ZK_LAUNCH(ctx, k_mark_solved, grid_for(n_out, 256), 256, 0, solved, v.wstep, (uint32_t)si, (uint64_t)out, (uint64_t)n_out); break; }
             const uint64_t r0 = p->h_hint_in0[h], r1 = p->h_hint_in1[h];
             ZK_CUDA(cudaMemsetAsync(p->counters, 0, (size_t)n_out * 4, ctx->stream));
             if (r1 > r0) ZK_LAUNCH(ctx, k_count_queries, grid_for(r1 - r0, 256), 256, 0, v, r0, r1, n_out, p->counters, h);
@@ -513,7 +580,7 @@ static int32_t run_schedule(zkpor_ctx *ctx, zkpor_program *p, zkpor_pk *pk, Fr *
         }
         case STEP_COMMIT: {
             const uint32_t h = (uint32_t)s.a, out = p->h_hint_out[h];
-            if (DRY) { ZK_LAUNCH(ctx, k_mark_solved, grid_for(1, 32), 32, 0, solved, (uint64_t)out, (uint64_t)1); break; }
+            if (DRY) { ZK_LAUNCH(ctx, k_mark_solved, grid_for(1, 32), 32, 0, solved, v.wstep, (uint32_t)si, (uint64_t)out, (uint64_t)1); break; }
             // Prove's override of the BSB22 placeholder: Pedersen-commit the private committed wires, hash the
             // commitment to the field; the proof of knowledge shares the sort of the committed values, so it is taken here as well
             if (pk == nullptr || !pk->has_commitment) { set_error("solve: the program has a commitment hint but no proving key with a commitment key was given"); return ZKPOR_ERR_INVALID_ARG; }
@@ -525,12 +592,42 @@ static int32_t run_schedule(zkpor_ctx *ctx, zkpor_program *p, zkpor_pk *pk, Fr *
         }
         }
     }
+    if (trace) {
+        cudaEventRecord(tev[p->steps.size()], ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        if (FILE *f = fopen(p->trace_path, "w")) {
+            fprintf(f, "step,kind,count,n_long,has_div,ms\n");
+            for (size_t si = 0; si < p->steps.size(); si++) {
+                float ms = 0.f; cudaEventElapsedTime(&ms, tev[si], tev[si + 1]);
+                const Step &s = p->steps[si];
+                fprintf(f, "%zu,%d,%llu,%llu,%d,%.4f\n", si, s.kind, (unsigned long long)(s.kind <= STEP_NARROW ? s.b - s.a : 1), (unsigned long long)s.n_long, (int)s.has_div, ms);
+            }
+            fclose(f);
+        }
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
     return solve_error(p, ctx, DRY ? "program_upload" : "solve");
 }
 
-int32_t solver_run(zkpor_ctx *ctx, zkpor_program *prog, zkpor_pk *pk, Fr *d_wires, G1XYZZ *commit, G1XYZZ *pok, bool *has_commit) {
+int32_t solver_run(zkpor_ctx *ctx, zkpor_program *prog, zkpor_pk *pk, Fr *d_wires, G1XYZZ *commit, G1XYZZ *pok, bool *has_commit, bool defer_tail) {
     *has_commit = prog->has_commit;
-    return run_schedule<false>(ctx, prog, pk, d_wires, nullptr, commit, pok);
+    return run_schedule<false>(ctx, prog, pk, d_wires, nullptr, commit, pok, defer_tail);
+}
+bool solver_tail_info(const zkpor_program *prog, SolverTail *out) {
+    if (prog->tail_step < 0) return false;
+    out->uid = prog->uid; out->mask = prog->tail_mask; out->wires = &prog->h_tail_wires; out->levels = prog->steps[(size_t)prog->tail_step].b - prog->steps[(size_t)prog->tail_step].a;
+    return true;
+}
+// the compute stream waits for the tail; its errors surface here.  A no-op when no tail is in flight.
+int32_t solver_tail_join(zkpor_ctx *ctx, zkpor_program *prog) {
+    if (!prog->tail_running) return ZKPOR_OK;
+    prog->tail_running = false;
+    ZK_CUDA(cudaStreamWaitEvent(ctx->stream, prog->tail_done, 0));
+    return solve_error(prog, ctx, "solve");
+}
+// error paths: nothing of the program may still be running when the caller returns
+void solver_tail_abandon(zkpor_ctx *ctx, zkpor_program *prog) {
+    if (prog && prog->tail_running) { cudaStreamSynchronize(ctx->tail_stream); prog->tail_running = false; }
 }
 zkpor_r1cs *program_matrices(zkpor_program *prog) { return prog->cs; }
 uint64_t program_inputs(const zkpor_program *prog) { return prog->n_public - 1 + prog->n_secret; }
@@ -562,6 +659,10 @@ int32_t zkpor_program_free(zkpor_ctx *ctx, zkpor_program *p) {
     void *ptrs[] = {p->aux_ptr, p->aux_wire, p->aux_coef, p->sched, p->lvl_start, p->hint_fn, p->hint_param, p->hint_out, p->hint_nout,
                     p->hint_in0, p->hint_in1, p->table_ptr, p->solve_e, p->err, p->counters, p->pend, p->step_div};
     for (void *q : ptrs) if (q) cudaFree(q);
+    if (p->tail_running) cudaStreamSynchronize(ctx->tail_stream);
+    for (void *q : {(void *)p->tail_wires, (void *)p->tail_mask, (void *)p->wstep}) if (q) cudaFree(q);
+    if (p->tail_go) cudaEventDestroy(p->tail_go);
+    if (p->tail_done) cudaEventDestroy(p->tail_done);
     p->wires.release(); p->abc.release();
     delete p;
     return ZKPOR_OK;
@@ -570,6 +671,20 @@ int32_t zkpor_program_free(zkpor_ctx *ctx, zkpor_program *p) {
 int32_t zkpor_program_stats(zkpor_program *prog, uint64_t out4[4]) {
     ZK_REQUIRE(prog && out4, "program_stats: null argument");
     for (int i = 0; i < 4; i++) out4[i] = prog->stats[i];
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_program_tail_info(zkpor_program *prog, uint64_t out3[3]) {
+    ZK_REQUIRE(prog && out3, "program_tail_info: null argument");
+    out3[0] = out3[1] = out3[2] = 0;
+    if (prog->tail_step >= 0) { const zk::Step &t = prog->steps[(size_t)prog->tail_step]; out3[0] = t.b - t.a; out3[1] = prog->n_tail_wires; out3[2] = prog->tail_after; }
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_program_tail_wires(zkpor_program *prog, uint32_t *out_wires, uint64_t cap) {
+    ZK_REQUIRE(prog && (out_wires || cap == 0), "program_tail_wires: null argument");
+    ZK_REQUIRE(cap >= prog->h_tail_wires.size(), "program_tail_wires: buffer too small (zkpor_program_tail_info gives the count)");
+    if (!prog->h_tail_wires.empty()) memcpy(out_wires, prog->h_tail_wires.data(), prog->h_tail_wires.size() * 4);
     return ZKPOR_OK;
 }
 
@@ -626,6 +741,7 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
     for (uint64_t t = 0; t < d->n_tables; t++) if (tptr[t] > tptr[t + 1] || tptr[t + 1] > d->n_aux_rows) return bad("table_ptr out of range");
     if (const char *e = getenv("ZKPOR_NARROW_MAX")) p->narrow_max = (uint32_t)std::max(1, atoi(e));
     if (const char *e = getenv("ZKPOR_NARROW_THREADS")) p->narrow_threads = std::min(NARROW_THREADS, std::max(32, atoi(e) & ~31));
+    p->trace_path = getenv("ZKPOR_SOLVE_TRACE");
     p->long_row = WIDE_LONG_ROW;
     if (const char *e = getenv("ZKPOR_WIDE_LONG_ROW")) p->long_row = (uint32_t)std::max(0, atoi(e));   // 0: every row takes a warp
     // schedule: instructions in level order, special hints lifted out as steps of their own
@@ -681,6 +797,7 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
         if (cudaMalloc((void **)&d_cls, std::max<size_t>(sched.size(), 1)) != cudaSuccess) { set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
         ProgView v0 = make_view(p, nullptr, nullptr);
         k_row_class<<<grid_for(sched.size(), 256), 256, 0, ctx->stream>>>(v0, (uint64_t)sched.size(), d_cls);
+        cudaStreamSynchronize(ctx->stream);
         rc = fetch(cls, (const uint8_t *)d_cls, sched.size());
         cudaFree(d_cls);
         if (rc != ZKPOR_OK) return fail(rc);
@@ -702,6 +819,8 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
     cudaMemsetAsync(solved, 0, d->n_wires, ctx->stream);
     cudaMemsetAsync(solved, 1, d->n_public + d->n_secret, ctx->stream);
     cudaMemsetAsync(p->solve_e, 0xFF, std::max<uint64_t>(d->n_constraints, 1) * 8, ctx->stream);
+    if (cudaMalloc((void **)&p->wstep, d->n_wires * 4) != cudaSuccess) { cudaFree(solved); set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
+    cudaMemsetAsync(p->wstep, 0, d->n_wires * 4, ctx->stream);
     rc = run_schedule<true>(ctx, p, nullptr, nullptr, solved, nullptr, nullptr);
     if (rc == ZKPOR_OK) {
         std::vector<uint8_t> sd;
@@ -718,6 +837,43 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
     }
     cudaFree(solved);
     if (rc != ZKPOR_OK) return fail(rc);
+    // the deferred tail: the last step, if it is a long run of narrow levels
+    uint64_t tail_min = 2048;
+    if (const char *e = getenv("ZKPOR_TAIL_MIN")) tail_min = (uint64_t)std::max(0, atoi(e));   // 0: never defer
+    if (tail_min > 0 && !p->steps.empty() && p->steps.back().kind == STEP_NARROW && p->steps.back().b - p->steps.back().a >= tail_min) {
+        const Step &t = p->steps.back();
+        const uint64_t p0 = lvl_start[t.a], p1 = lvl_start[t.b];
+        const uint32_t mark = (uint32_t)p->steps.size();       // wstep of the wires the last step solves
+        unsigned long long *d_cur = nullptr; uint32_t *d_dep = nullptr;
+        if (cudaMalloc((void **)&d_cur, 16) != cudaSuccess) { set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
+        d_dep = (uint32_t *)(d_cur + 1);
+        cudaMemsetAsync(d_cur, 0, 16, ctx->stream);
+        ProgView v = make_view(p, nullptr, nullptr);
+        k_tail_scan<<<grid_for(p1 - p0, 128), 128, 0, ctx->stream>>>(v, p0, p1, mark, nullptr, d_cur, d_dep);
+        unsigned long long hn[2] = {0, 0};
+        cudaMemcpyAsync(hn, d_cur, 16, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        p->n_tail_wires = hn[0];
+        p->tail_after = std::min<uint64_t>((uint32_t)hn[1], p->steps.size() - 1);
+        const uint64_t mask_words = (d->n_wires + 31) / 32;
+        if (cudaMalloc((void **)&p->tail_wires, std::max<uint64_t>(p->n_tail_wires, 1) * 4) != cudaSuccess ||
+            cudaMalloc((void **)&p->tail_mask, mask_words * 4) != cudaSuccess) { cudaFree(d_cur); set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
+        cudaMemsetAsync(d_cur, 0, 8, ctx->stream);
+        cudaMemsetAsync(p->tail_mask, 0, mask_words * 4, ctx->stream);
+        k_tail_scan<<<grid_for(p1 - p0, 128), 128, 0, ctx->stream>>>(v, p0, p1, mark, p->tail_wires, d_cur, d_dep);
+        cudaStreamSynchronize(ctx->stream);   // the context's stream does not synchronise with the blocking copy below
+        rc = fetch(p->h_tail_wires, (const uint32_t *)p->tail_wires, p->n_tail_wires);
+        cudaFree(d_cur);
+        if (rc != ZKPOR_OK) return fail(rc);
+        std::sort(p->h_tail_wires.begin(), p->h_tail_wires.end());
+        cudaMemcpy(p->tail_wires, p->h_tail_wires.data(), p->n_tail_wires * 4, cudaMemcpyHostToDevice);
+        if (p->n_tail_wires) k_wire_mask<<<grid_for(p->n_tail_wires, 256), 256, 0, ctx->stream>>>(p->tail_wires, p->n_tail_wires, p->tail_mask);
+        if (cudaEventCreateWithFlags(&p->tail_go, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&p->tail_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("program_upload: tail setup failed"); return fail(ZKPOR_ERR_CUDA); }
+        p->tail_step = (int64_t)p->steps.size() - 1;
+    }
+    cudaFree(p->wstep); p->wstep = nullptr;
+    { static uint64_t next_uid = 1; p->uid = __atomic_fetch_add(&next_uid, 1, __ATOMIC_RELAXED); }
     *out = p;
     return ZKPOR_OK;
 }
@@ -739,7 +895,7 @@ int32_t zkpor_r1cs_solve(zkpor_ctx *ctx, zkpor_program *prog, zkpor_pk *pk, cons
     stage_begin(ctx, ST_SOLVE);
     G1XYZZ commit = G1XYZZ::inf(), pok = G1XYZZ::inf();
     bool has_commit = false;
-    ZK_TRY(solver_run(ctx, prog, pk, w, &commit, &pok, &has_commit));
+    ZK_TRY(solver_run(ctx, prog, pk, w, &commit, &pok, &has_commit, false));
     // a = L w, b = R w, c = O w and gnark's satisfaction check
     const size_t bytes = prog->n_rows * sizeof(Fr);
     void *outs[3] = {out_a, out_b, out_c};
