@@ -71,6 +71,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the discrete-log check of the timed proof (it costs ~1 min of host time at 2^26)")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-proof-across-N-GPUs measurement")
+    ap.add_argument("--provers", type=int, default=2, help="provers per GPU (each with its own context, key and program), proving independent batches concurrently")
     return ap.parse_args()
 
 
@@ -272,7 +273,7 @@ def check_proof_by_discrete_logs(orc, ctx, sh, wires_dev, a, b, c, proof, r, s):
 class Workload:
     """circuit + key + inputs of one domain size, resident in HBM"""
 
-    def __init__(self, torch, zk, ctx, log_n, seed=0xB200):
+    def __init__(self, torch, zk, ctx, log_n, seed=0xB200, keep_generator=True):
         t0 = time.perf_counter()
         self.torch, self.zk, self.ctx, self.log_n = torch, zk, ctx, log_n
         self.cs_mod, self.flat, self.params = build_circuit(zk, log_n, xp=torch, device="cuda")
@@ -281,6 +282,14 @@ class Workload:
         self.pk, self.arrays, _ = build_key(torch, zk, ctx, self.sh)
         self.inputs_plain = self.cs_mod.draw_inputs(self.flat, seed)
         self.inputs = inputs_to_mont(torch, ctx, self.inputs_plain)
+        self.text = self.describe()
+        if not keep_generator:
+            # the library holds its own copies of the key and of the constraint system: drop the generator's (~50 GB at 2^26)
+            self.arrays = None
+            for k, v in list(self.flat.items()):
+                if hasattr(v, "device"):
+                    self.flat[k] = None
+            torch.cuda.empty_cache()
         self.setup_s = time.perf_counter() - t0
 
     def describe(self):
@@ -365,10 +374,24 @@ def main():
         return 0
 
     # ---------------------------------------------------------------- native arm
-    wl = Workload(torch, zk, ctx, args.log_n)
+    # P provers per GPU, each with its own context (streams, scratch), key and program, proving independent batches from P host
+    # threads: while one proof is in its multiplications (throughput-bound kernels that fill the SMs) another is in its solve (a
+    # latency chain of ~8 000 small launches), as the reference runs several prover processes per machine (README.md:126).
+    P = max(1, args.provers)
+    wl = Workload(torch, zk, ctx, args.log_n, keep_generator=(world > 1 and not args.no_sharded))
     sh, pk, prog = wl.sh, wl.pk, wl.prog
-    workload = wl.describe()
-    stream = torch.cuda.ExternalStream(ctx.stream())
+    workload = wl.text
+    provers = [(ctx, wl)]
+    for _ in range(1, P):
+        free_gb = torch.cuda.mem_get_info()[0] / 1e9
+        used_gb = (torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 1e9
+        if free_gb < 1.6 * used_gb / len(provers) + 4:    # a prover's scratch grows by about half again during its first proofs
+            print(f"bench: {free_gb:.0f} GB free, a prover needs ~{1.6 * used_gb / len(provers):.0f} GB: running {len(provers)} prover(s) per GPU", file=sys.stderr)
+            break
+        c2 = zk.Context(local)
+        provers.append((c2, Workload(torch, zk, c2, args.log_n, keep_generator=False)))
+    P = len(provers)
+    hbm_gb = (torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 1e9
 
     def step(inputs):
         return pk.prove_solve(prog, inputs, r, s)
@@ -379,50 +402,80 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(n_steps, inputs, fn=None):
-        fn = fn or step
+    def run(n_steps, inputs_of, fn=None):
+        """n_steps proofs by every prover (fn: prover 0 only, one thread); device time between two full-device synchronisations"""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        who = provers if fn is None else provers[:1]
+        outs, stages, errs = [[] for _ in who], [], []
+
+        def work(i):
+            c, w = who[i]
+            try:
+                for _ in range(n_steps):
+                    outs[i].append(fn(inputs_of(w)) if fn is not None else w.pk.prove_solve(w.prog, inputs_of(w), r, s))
+                    if i == 0:
+                        stages.append(c.last_timings())
+            except Exception as e:     # surfaces below: a thread must not die silently
+                errs.append(e)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(1, len(who))]
         barrier()
-        e0.record(stream)
+        e0.record()
         t0 = time.perf_counter()
-        stages = []
-        for _ in range(n_steps):
-            proof = fn(inputs)
-            stages.append(ctx.last_timings())
-        e1.record(stream)
+        for t in th:
+            t.start()
+        work(0)
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        e1.record()
         barrier()
         wall = time.perf_counter() - t0
+        if errs:
+            raise errs[0]
         ms = max(e0.elapsed_time(e1), 0.0)
         if dist is not None:
             t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-        return ms, wall, proof, stages
+        proofs = [p for o in outs for p in o]
+        assert all(p == proofs[0] for p in proofs), "provers disagree on the proof of the same batch"
+        return ms, wall, proofs[0], stages
 
-    for _ in range(args.warmup):
-        proof = step(wl.inputs)
+    for c, w in provers:
+        for _ in range(args.warmup):
+            proof = w.pk.prove_solve(w.prog, w.inputs, r, s)
     sampler = ClockSampler(local); sampler.start()
-    ctx.kernel_timing(True, classes=[0, 1, 2, 3])   # not the solver's ~8 000 launches per proof: an event pair per launch is not free
-    l0 = ctx.launch_count()
+    ctx.kernel_timing(True, classes=[0, 1, 2, 3, 6])   # not the solver's ~8 000 wide launches per proof: an event pair per launch is not free
+    l0 = [c.launch_count() for c, _ in provers]
     torch.cuda.cudart().cudaProfilerStart()          # `ncu --profile-from-start off` captures exactly the timed steps
-    ms, wall, proof, stages = run(args.steps, wl.inputs)
+    ms, wall, proof, stages = run(args.steps, lambda w: w.inputs)
     torch.cuda.cudart().cudaProfilerStop()
-    launches = ctx.launch_count() - l0
-    kstats = {name: ctx.kernel_stats(k) for k, name in enumerate(["accumulate_g1", "accumulate_g2", "ntt_pass", "digits_scatter"])}
+    launches = sum(c.launch_count() - l for (c, _), l in zip(provers, l0))
+    kstats = {name: ctx.kernel_stats(k) for k, name in ((0, "accumulate_g1"), (1, "accumulate_g2"), (2, "ntt_pass"), (3, "digits_scatter"), (6, "solver_tail"))}
     ctx.kernel_timing(False)
     clocks = sampler.stop()
-    proofs_per_step = world
+    proofs_per_step = world * P
     value = proofs_per_step * args.steps / (ms / 1e3) * 3600.0
+    # latency and stage breakdown of ONE proof alone on the GPU (the timed region runs P provers per GPU)
+    solo_ms, _, _, stages = run(1, lambda w: w.inputs, step)
     solve_ms = float(np.mean([st.get("solve", 0.0) for st in stages]))
 
     # ---- e2e: pinned host inputs through the same call
     e2e = None
     if not args.no_e2e:
-        hin = wl.inputs.cpu().pin_memory()
-        inputs_h = hin.numpy()
-        step(inputs_h)
-        ems, ewall, eproof, _ = run(args.steps, inputs_h)
+        for c, w in provers:
+            w.hin = w.inputs.cpu().pin_memory()
+            w.inputs_h = w.hin.numpy()
+            w.pk.prove_solve(w.prog, w.inputs_h, r, s)
+        ems, ewall, eproof, _ = run(args.steps, lambda w: w.inputs_h)
         assert eproof == proof, "e2e proof differs from the device-resident proof"
-        e2e = {"value": proofs_per_step * args.steps / (ems / 1e3) * 3600.0, "unit": "proofs/hour", "h2d_bytes_per_step": hin.numel() * 8 * proofs_per_step,
+        e2e = {"value": proofs_per_step * args.steps / (ems / 1e3) * 3600.0, "unit": "proofs/hour", "h2d_bytes_per_step": wl.hin.numel() * 8 * proofs_per_step,
                "d2h_bytes_per_step": len(proof) * proofs_per_step, "ms_per_step": ems / args.steps}
+
+    # the extra provers have done their part: their ~85 GB each go back before the checks below allocate
+    for c, w in provers[1:]:
+        w.close(); c.close()
+    provers = provers[:1]
+    torch.cuda.empty_cache()
 
     # ---- parity of the TIMED proof: exact, by discrete logs (oracle = checker)
     parity = None
@@ -455,11 +508,11 @@ def main():
         for _ in range(max(1, args.warmup)):
             sproof = sstep(wl.inputs)
         c0 = ctx.comm_info()
-        sms, swall, sproof, sstages = run(args.steps, wl.inputs, sstep)
+        sms, swall, sproof, sstages = run(args.steps, lambda w: w.inputs, sstep)
         c1 = ctx.comm_info()
         same = torch.tensor([1 if sproof == proof else 0], device="cuda"); dist.all_reduce(same, op=dist.ReduceOp.MIN)
         st = {k: float(np.mean([x.get(k, 0.0) for x in sstages])) for k in sstages[0]}
-        one_ms = ms / args.steps
+        one_ms = solo_ms
         sharded = {"ms_per_proof": sms / args.steps, "speedup_vs_1": one_ms / (sms / args.steps), "one_gpu_ms_per_proof": one_ms,
                    "solve_ms": st.get("solve", 0.0), "after_solve_ms": sms / args.steps - st.get("solve", 0.0), "ntt_ms": st.get("ntt", 0.0),
                    "proof_identical_to_one_gpu_on_every_rank": bool(same.item()),
@@ -503,12 +556,12 @@ def main():
 
     line = {"metric": "proofs/hour", "value": value, "unit": "proofs/hour", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-            "config": {"workload": workload, "parallelism": "single GPU" if world == 1 else f"{world} independent proofs per step, one per GPU (full key per GPU), no data-path collective",
-                       "proofs_per_step": proofs_per_step, "solver_schedule": prog.stats(),
+            "config": {"workload": workload, "parallelism": f"{P} provers per GPU (own context, key and program each; independent batches from {P} host threads)" + ("" if world == 1 else f" x {world} GPUs, no data-path collective"),
+                       "proofs_per_step": proofs_per_step, "provers_per_gpu": P, "hbm_in_use_gb": hbm_gb, "solver_schedule": prog.stats(),
                        "l2": "inputs (>= 2 GB per vector, 21 GB key, ~6 GB constraint system) are far larger than the 126 MB L2; no explicit flush needed",
                        "key": "synthetic key in HBM: points (k0 + i*d)*G per array", "timing": "CUDA events on the library stream, max over ranks",
                        "setup_s": wl.setup_s},
-            "solve_ms": solve_ms, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "modmul_roofline": modmul, "kernel_breakdown": breakdown,
+            "solve_ms": solve_ms, "one_proof_alone_ms": solo_ms, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "modmul_roofline": modmul, "kernel_breakdown": breakdown,
             "stage_ms": {k: float(np.mean([st.get(k, 0.0) for st in stages])) for k in (stages[0] if stages else {})},
             "wall_ms_per_step": wall / args.steps * 1e3, "proof_sha": __import__("hashlib").sha256(proof).hexdigest()[:16]}
     if e2e:
@@ -518,7 +571,9 @@ def main():
     if sharded:
         line["sharded"] = sharded
     if rank == 0 and world == 1 and not args.no_cpu:
-        wl.close(); del wl, pk, prog
+        for c, w in provers:
+            w.close()
+        del wl, pk, prog, provers
         torch.cuda.empty_cache()
         res = cpu_full_prove(torch, zk, ctx, args.cpu_log_n)
         scale = sh["n_constraints"] / res["n_constraints"]

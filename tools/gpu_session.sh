@@ -24,7 +24,9 @@ for st in $steps; do
     bench22n) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NGPU --log-n 22 --no-cpu > gpurun_out/s_bench22_n$NGPU.json 2> gpurun_out/s_bench22_n$NGPU.err; echo "bench22n rc=$?"; tail -c 3000 gpurun_out/s_bench22_n$NGPU.json; tail -5 gpurun_out/s_bench22_n$NGPU.err ;;
     bench26n) timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NGPU --no-cpu --no-parity > gpurun_out/s_bench26_n$NGPU.json 2> gpurun_out/s_bench26_n$NGPU.err; echo "bench26n rc=$?"; tail -c 3000 gpurun_out/s_bench26_n$NGPU.json; tail -5 gpurun_out/s_bench26_n$NGPU.err ;;
     solvertrace26) ZKPOR_SOLVE_TRACE=gpurun_out/solve_trace26.csv timeout 900 python tools/solver_bench.py 26 96:512:9 > gpurun_out/s_solvertrace26.log 2>&1; echo "solvertrace26 rc=$?"; tail -40 gpurun_out/s_solvertrace26.log | cut -c1-400 ;;
-    ncu_narrow) timeout 900 ncu --set full --import-source on --clock-control none --kernel-id ::regex:k_solve_narrow:6 -f -o gpurun_out/r02_narrow python tools/solver_bench.py 22 96:512:9 > gpurun_out/s_ncu_narrow.log 2>&1; echo "ncu narrow rc=$?"; tail -3 gpurun_out/s_ncu_narrow.log | cut -c1-300 ;;
+    inflight26) timeout 900 python tools/inflight_bench.py 26 2 3 > gpurun_out/s_inflight26.log 2>&1; echo "inflight26 rc=$?"; tail -6 gpurun_out/s_inflight26.log | cut -c1-400 ;;
+    inflight22) timeout 600 python tools/inflight_bench.py 22 2 3 > gpurun_out/s_inflight22.log 2>&1; echo "inflight22 rc=$?"; tail -6 gpurun_out/s_inflight22.log | cut -c1-400 ;;
+    ncu_narrow) timeout 900 ncu --set full --import-source on --clock-control none -k k_solve_narrow --launch-skip 6 -c 3 -f -o gpurun_out/r02_narrow python tools/solver_bench.py 22 96:512:9 > gpurun_out/s_ncu_narrow.log 2>&1; echo "ncu narrow rc=$?"; tail -3 gpurun_out/s_ncu_narrow.log | cut -c1-300 ;;
     *) echo "unknown step $st" ;;
   esac
 done

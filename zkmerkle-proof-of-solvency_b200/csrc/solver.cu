@@ -96,6 +96,85 @@ __device__ __forceinline__ Fr term_acc(const ProgView &v, const Fr &acc, uint32_
     return Fr::add(acc, Fr::mul(v.coeffs[cid], x));
 }
 
+// ---- unreduced sums.  A linear expression of a Poseidon row has ~80 terms, spread over the lanes of a group: reducing modulo r
+// after every addition of the tree sum (an addition, a comparison and a conditional subtraction of eight limbs, per shuffle step) cost
+// more than the products.  The lanes therefore add their residues as plain integers in nine limbs (room for 2^32 terms), the tree
+// adds nine limbs per step, and ONE lane reduces the total: S = hi * 2^256 + lo, hi * 2^256 mod r = the Montgomery form of hi (a
+// 64-entry table in constant memory; a product beyond it), then lo + table[hi] < 2^256 + r comes below r by conditional
+// subtractions of 4r, 2r and r.
+struct Wide9 { uint32_t l[9]; };
+__constant__ Fr c_hi_mont[64];                    // c_hi_mont[k] = k * 2^256 mod r
+__device__ __forceinline__ Wide9 w9_zero() { Wide9 a; for (int i = 0; i < 9; i++) a.l[i] = 0; return a; }
+__device__ __forceinline__ void w9_add(Wide9 &a, const Fr &x) {
+    a.l[0] = ptx::add_cc(a.l[0], x.l[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) a.l[i] = ptx::addc_cc(a.l[i], x.l[i]);
+    a.l[8] = ptx::addc(a.l[8], 0u);
+}
+__device__ __forceinline__ void w9_addw(Wide9 &a, const Wide9 &b) {
+    a.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) a.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+    a.l[8] = ptx::addc(a.l[8], b.l[8]);
+}
+// v -= k*r when v >= k*r (v: nine limbs, k*r < 2^256)
+template <int K>
+__device__ __forceinline__ void w9_csub(Wide9 &v) {
+    Wide9 d;
+    uint32_t m[8]; uint32_t carry = 0;                    // K * r, K = 1, 2, 4
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const uint64_t t = (uint64_t)FrParams::M(i) * K + carry; m[i] = (uint32_t)t; carry = (uint32_t)(t >> 32); }
+    d.l[0] = ptx::sub_cc(v.l[0], m[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) d.l[i] = ptx::subc_cc(v.l[i], m[i]);
+    d.l[8] = ptx::subc_cc(v.l[8], 0u);
+    const uint32_t borrow = ptx::subc(0u, 0u);            // 0 or 0xffffffff
+#pragma unroll
+    for (int i = 0; i < 9; i++) v.l[i] = borrow ? v.l[i] : d.l[i];
+}
+__device__ __forceinline__ Fr w9_reduce(const Wide9 &s) {
+    const uint32_t hi = s.l[8];
+    const Fr t = hi < 64 ? c_hi_mont[hi] : Fr::from_u64(hi);
+    Wide9 v;
+    v.l[0] = ptx::add_cc(s.l[0], t.l[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) v.l[i] = ptx::addc_cc(s.l[i], t.l[i]);
+    v.l[8] = ptx::addc(0u, 0u);
+    w9_csub<4>(v); w9_csub<2>(v); w9_csub<1>(v);   // 2^256 < 5.3 r, so v < 6.3 r: minus 4r if possible -> < 4r; minus 2r -> < 2r; minus r -> < r
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = v.l[i];
+    return r;
+}
+// one term: the coefficients 1 and -1 skip the product
+__device__ __forceinline__ void term_w9(const ProgView &v, Wide9 &acc, uint32_t cid, const Fr &x) {
+    if (cid == v.one_id) w9_add(acc, x);
+    else if (cid == v.minus_one_id) w9_add(acc, Fr::neg(x));
+    else w9_add(acc, Fr::mul(v.coeffs[cid], x));
+}
+// tree sum over the G lanes of a group; valid on lane 0
+template <int G>
+__device__ __forceinline__ Wide9 group_sum_w9(Wide9 acc, unsigned mask) {
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        Wide9 o;
+#pragma unroll
+        for (int i = 0; i < 9; i++) o.l[i] = __shfl_down_sync(mask, acc.l[i], off, G);
+        w9_addw(acc, o);
+    }
+    return acc;
+}
+__device__ __forceinline__ Wide9 lane_dot_w9(const ProgView &v, const uint64_t *ptr, const uint32_t *wire, const uint32_t *coef, uint64_t row, uint64_t skip,
+                                             int lane, int stride) {
+    Wide9 acc = w9_zero();
+    const uint64_t e1 = ptr[row + 1];
+    for (uint64_t e = ptr[row] + lane; e < e1; e += stride) {
+        if (e == skip) continue;
+        term_w9(v, acc, coef[e], v.w[wire[e]]);
+    }
+    return acc;
+}
+
 // tree sum over the G lanes of a group; valid on lane 0
 template <int G>
 __device__ __forceinline__ Fr group_sum(Fr acc, unsigned mask) {
@@ -125,6 +204,10 @@ __device__ __forceinline__ Fr lane_dot(const ProgView &v, const uint64_t *ptr, c
 template <int G>
 __device__ __forceinline__ Fr group_dot(const ProgView &v, const uint64_t *ptr, const uint32_t *wire, const uint32_t *coef, uint64_t row,
                                         uint64_t skip, int lane, unsigned mask) {
+    if (G >= 8) {   // long rows: unreduced sums, one reduction (lane 0 of the group)
+        const Wide9 s = group_sum_w9<G>(lane_dot_w9(v, ptr, wire, coef, row, skip, lane, G), mask);
+        return lane == 0 ? w9_reduce(s) : Fr::zero();
+    }
     return group_sum<G>(lane_dot(v, ptr, wire, coef, row, skip, lane, G), mask);
 }
 
@@ -367,7 +450,7 @@ static const int NARROW_SUB = 4;                  // warps per side at most
 static const int NARROW_SPLIT_INSTR = NARROW_THREADS / 32 / 3;   // instructions of a level that can be split by side
 template <bool DRY>
 __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow(ProgView v, uint64_t l0, uint64_t l1) {
-    __shared__ Fr part[NARROW_SPLIT_INSTR][3][NARROW_SUB];
+    __shared__ uint32_t part[NARROW_SPLIT_INSTR][3][NARROW_SUB][12];   // nine limbs of an unreduced partial sum
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (uint64_t l = l0; l < l1; l++) {
         if (l + 3 < l1) {
@@ -413,16 +496,24 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow(ProgView v, uin
                 se = v.solve_e[packed];
                 if (se != SOLVE_NONE) {
                     const uint64_t skip = (int)(se >> 62) == side ? (se & ((1ull << 62) - 1)) : SOLVE_NONE;
-                    const Fr acc = group_sum<32>(lane_dot(v, v.ptr[side], v.wire[side], v.coef[side], packed, skip, prt * 32 + lane, sub * 32), 0xFFFFFFFFu);
-                    if (lane == 0) part[ins][side][prt] = acc;
+                    const Wide9 acc = group_sum_w9<32>(lane_dot_w9(v, v.ptr[side], v.wire[side], v.coef[side], packed, skip, prt * 32 + lane, sub * 32), 0xFFFFFFFFu);
+                    if (lane == 0) for (int i = 0; i < 9; i++) part[ins][side][prt][i] = acc.l[i];
                 }
             }
         }
         __syncthreads();
-        if (ins < k && rem == 0 && lane == 0 && !(packed & HINT_BIT) && se != SOLVE_NONE) {
-            Fr abc[3];
-            for (int sd = 0; sd < 3; sd++) { abc[sd] = part[ins][sd][0]; for (int q = 1; q < sub; q++) abc[sd] = Fr::add(abc[sd], part[ins][sd][q]); }
-            finish_instr(v, packed, (int)(se >> 62), se & ((1ull << 62) - 1), abc[0], abc[1], abc[2], NO_SLOT);
+        if (ins < k && rem == 0 && !(packed & HINT_BIT) && se != SOLVE_NONE) {
+            // lanes 0, 1, 2 of the instruction's first warp total and reduce one side each; lane 0 finishes
+            Fr mine = Fr::zero();
+            if (lane < 3) {
+                Wide9 t = w9_zero();
+                for (int q = 0; q < sub; q++) { Wide9 o; for (int i = 0; i < 9; i++) o.l[i] = part[ins][lane][q][i]; w9_addw(t, o); }
+                mine = w9_reduce(t);
+            }
+            Fr b, c;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { b.l[i] = __shfl_sync(0xFFFFFFFFu, mine.l[i], 1); c.l[i] = __shfl_sync(0xFFFFFFFFu, mine.l[i], 2); }
+            if (lane == 0) finish_instr(v, packed, (int)(se >> 62), se & ((1ull << 62) - 1), mine, b, c, NO_SLOT);
         }
         __syncthreads();
     }
@@ -812,6 +903,11 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
             p->stats_long += st.n_long;
         }
         if (cudaMemcpy(p->sched, sched.data(), sched.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("program_upload: schedule copy failed"); return fail(ZKPOR_ERR_CUDA); }
+    }
+    {   // table of the unreduced sums' reduction (w9_reduce)
+        Fr tab[64];
+        for (uint64_t k = 0; k < 64; k++) tab[k] = Fr::from_u64(k);
+        if (cudaMemcpyToSymbol(c_hi_mont, tab, sizeof tab) != cudaSuccess) { set_error("program_upload: constant table upload failed"); return fail(ZKPOR_ERR_CUDA); }
     }
     // dry run: which wire does every R1C instruction solve for
     uint8_t *solved = nullptr;
