@@ -204,6 +204,9 @@ typedef struct {
 } zkpor_program_desc;
 int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *desc, zkpor_program **out);
 int32_t zkpor_program_free(zkpor_ctx *ctx, zkpor_program *prog);
+/* the program's three matrices as a zkpor_r1cs (for zkpor_r1cs_eval / zkpor_groth16_prove_wires on wires solved elsewhere); the handle
+ * is borrowed: it lives as long as the program and must not be passed to zkpor_r1cs_free */
+int32_t zkpor_program_r1cs(zkpor_program *prog, zkpor_r1cs **out);
 /* number of schedule steps by type: wide level launches, fused runs of narrow levels, levels inside those runs, count hints */
 int32_t zkpor_program_stats(zkpor_program *prog, uint64_t out4[4]);
 /* The deferred tail of the schedule (0, 0, 0 when the program has none): when the schedule ends in a long run of narrow levels -- in

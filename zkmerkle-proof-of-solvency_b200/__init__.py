@@ -645,9 +645,9 @@ class R1CS:
                                        _ptr(tab), C.c_uint64(tab.shape[0]), C.byref(self._h)))
 
     def close(self):
-        if self._h:
+        if self._h and not getattr(self, "_borrowed", False):
             lib().zkpor_r1cs_free(self.ctx._h, self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -737,6 +737,13 @@ class Program:
         _check(lib().zkpor_program_tail_info(self._h, t))
         return dict(wide_levels=out[0], narrow_runs=out[1], narrow_levels=out[2], count_hints=out[3],
                     deferred_tail=dict(levels=t[0], wires=t[1], starts_before_step=t[2]))
+
+    def r1cs(self) -> "R1CS":
+        """the program's matrices as an R1CS handle (borrowed: valid while the program lives; closing it is a no-op)"""
+        cs = R1CS.__new__(R1CS)
+        cs.ctx, cs.n_constraints, cs._h, cs._borrowed = self.ctx, self.n_constraints, C.c_void_p(), True
+        _check(lib().zkpor_program_r1cs(self._h, C.byref(cs._h)))
+        return cs
 
     def tail_wires(self) -> np.ndarray:
         n = self.stats()["deferred_tail"]["wires"]

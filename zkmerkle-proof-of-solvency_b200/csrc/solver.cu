@@ -448,50 +448,70 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 // one lane finishes (a*b, the subtraction, the store).  Two barriers per level instead of one, a third of the dependent products.
 static const int NARROW_SUB = 4;                  // warps per side at most
 static const int NARROW_SPLIT_INSTR = NARROW_THREADS / 32 / 3;   // instructions of a level that can be split by side
+// static data of the levels after l into L1, by `count` warps of which this is number `rank`: schedule entries of level l+3, row
+// pointers of level l+2, term lists of level l+1
+__device__ __forceinline__ void narrow_prefetch(const ProgView &v, uint64_t l, uint64_t l1, int rank, int count, int lane) {
+    if (l + 3 < l1) {
+        const uint64_t s0 = v.lvl_start[l + 3], s1 = v.lvl_start[l + 4];
+        for (uint64_t p = s0 + (uint64_t)(rank * 32 + lane) * 32; p < s1; p += (uint64_t)count * 32 * 32) prefetch_l1(v.sched + p);
+    }
+    if (l + 2 < l1) {
+        const uint64_t s0 = v.lvl_start[l + 2], s1 = v.lvl_start[l + 3];
+        for (uint64_t p = s0 + rank; p < s1; p += count) {
+            const uint32_t packed = v.sched[p];
+            if (packed & HINT_BIT) { if (lane == 0) { prefetch_l1(v.hint_in0 + (packed & ~HINT_BIT)); prefetch_l1(v.hint_out + (packed & ~HINT_BIT)); } }
+            else if (lane < 3) prefetch_l1(v.ptr[lane] + packed);
+            else if (lane == 3) prefetch_l1(v.solve_e + packed);
+        }
+    }
+    if (l + 1 < l1) {
+        const uint64_t s0 = v.lvl_start[l + 1], s1 = v.lvl_start[l + 2];
+        for (uint64_t p = s0 + rank; p < s1; p += count) {
+            const uint32_t packed = v.sched[p];
+            if (packed & HINT_BIT) continue;
+            for (int side = 0; side < 3; side++) {
+                const uint64_t e0 = v.ptr[side][packed], e1 = v.ptr[side][packed + 1];
+                for (uint64_t e = (e0 & ~31ull) + (uint64_t)lane * 32; e < e1; e += 32 * 32) { prefetch_l1(v.wire[side] + e); prefetch_l1(v.coef[side] + e); }
+            }
+        }
+    }
+}
+
 template <bool DRY>
 __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow(ProgView v, uint64_t l0, uint64_t l1) {
     __shared__ uint32_t part[NARROW_SPLIT_INSTR][3][NARROW_SUB][12];   // nine limbs of an unreduced partial sum
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // Everything that maps a warp to its role is worked out once: a level must not pay runtime divisions (they were 15 % of the
+    // kernel's instructions).  subs: 4 bits per level width k = 1..7 -> warps per side; role[s-1]: this warp's (instruction, side,
+    // part) when a side is split over s warps.
+    uint32_t subs = 0, role[NARROW_SUB];
+    for (int k = 1; k <= 7; k++) subs |= (uint32_t)(DRY || 3 * k > nwarps ? 0 : min(NARROW_SUB, nwarps / (3 * k))) << (4 * k);
+#pragma unroll
+    for (int sb = 1; sb <= NARROW_SUB; sb++) {
+        const int per = 3 * sb, ins = warp / per, rem = warp - ins * per, side = rem / sb, prt = rem - side * sb;
+        role[sb - 1] = (uint32_t)ins | ((uint32_t)side << 8) | ((uint32_t)prt << 16) | ((uint32_t)(rem == 0) << 24);
+    }
     for (uint64_t l = l0; l < l1; l++) {
-        if (l + 3 < l1) {
-            const uint64_t s0 = v.lvl_start[l + 3], s1 = v.lvl_start[l + 4];
-            for (uint64_t p = s0 + (uint64_t)threadIdx.x * 32; p < s1; p += (uint64_t)blockDim.x * 32) prefetch_l1(v.sched + p);
-        }
-        if (l + 2 < l1) {
-            const uint64_t s0 = v.lvl_start[l + 2], s1 = v.lvl_start[l + 3];
-            for (uint64_t p = s0 + warp; p < s1; p += nwarps) {
-                const uint32_t packed = v.sched[p];
-                if (packed & HINT_BIT) { if (lane == 0) { prefetch_l1(v.hint_in0 + (packed & ~HINT_BIT)); prefetch_l1(v.hint_out + (packed & ~HINT_BIT)); } }
-                else if (lane < 3) prefetch_l1(v.ptr[lane] + packed);
-                else if (lane == 3) prefetch_l1(v.solve_e + packed);
-            }
-        }
-        if (l + 1 < l1) {
-            const uint64_t s0 = v.lvl_start[l + 1], s1 = v.lvl_start[l + 2];
-            for (uint64_t p = s0 + warp; p < s1; p += nwarps) {
-                const uint32_t packed = v.sched[p];
-                if (packed & HINT_BIT) continue;
-                for (int side = 0; side < 3; side++) {
-                    const uint64_t e0 = v.ptr[side][packed], e1 = v.ptr[side][packed + 1];
-                    for (uint64_t e = (e0 & ~31ull) + (uint64_t)lane * 32; e < e1; e += 32 * 32) { prefetch_l1(v.wire[side] + e); prefetch_l1(v.coef[side] + e); }
-                }
-            }
-        }
         const uint64_t s0 = v.lvl_start[l], s1 = v.lvl_start[l + 1];
         const int k = (int)(s1 - s0);
-        const int sub = DRY || 3 * k > nwarps ? 0 : min(NARROW_SUB, nwarps / (3 * k));
+        const int sub = k <= 7 ? (int)((subs >> (4 * k)) & 15u) : 0;
         if (sub == 0) {
+            narrow_prefetch(v, l, l1, warp, nwarps, lane);
             for (uint64_t p = s0 + warp; p < s1; p += nwarps) exec_instr<32, DRY>(v, v.sched[p], lane, 0xFFFFFFFFu, NO_SLOT, NO_SLOT);
             __syncthreads();
             continue;
         }
-        // split mode: warp -> (instruction, side, part)
-        const int per = 3 * sub, ins = warp / per, rem = warp - ins * per, side = rem / sub, prt = rem - side * sub;
+        // split mode: warp -> (instruction, side, part); the warps beyond the 3 * k * sub working ones prefetch
+        const uint32_t rl = sub == 1 ? role[0] : sub == 2 ? role[1] : sub == 3 ? role[2] : role[3];
+        const int ins = (int)(rl & 255u), side = (int)((rl >> 8) & 255u), prt = (int)((rl >> 16) & 255u);
+        const bool first = (rl >> 24) != 0;
+        const int working = 3 * k * sub;
         uint32_t packed = HINT_BIT;
         uint64_t se = SOLVE_NONE;
-        if (ins < k) {
+        if (warp >= working) narrow_prefetch(v, l, l1, warp - working, nwarps - working, lane);
+        else {
             packed = v.sched[s0 + ins];
-            if (packed & HINT_BIT) { if (rem == 0 && lane == 0) exec_hint<false>(v, packed & ~HINT_BIT, NO_SLOT, NO_SLOT); }
+            if (packed & HINT_BIT) { if (first && lane == 0) exec_hint<false>(v, packed & ~HINT_BIT, NO_SLOT, NO_SLOT); }
             else {
                 se = v.solve_e[packed];
                 if (se != SOLVE_NONE) {
@@ -502,7 +522,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow(ProgView v, uin
             }
         }
         __syncthreads();
-        if (ins < k && rem == 0 && !(packed & HINT_BIT) && se != SOLVE_NONE) {
+        if (warp < working && first && !(packed & HINT_BIT) && se != SOLVE_NONE) {
             // lanes 0, 1, 2 of the instruction's first warp total and reduce one side each; lane 0 finishes
             Fr mine = Fr::zero();
             if (lane < 3) {
@@ -514,6 +534,9 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow(ProgView v, uin
 #pragma unroll
             for (int i = 0; i < 8; i++) { b.l[i] = __shfl_sync(0xFFFFFFFFu, mine.l[i], 1); c.l[i] = __shfl_sync(0xFFFFFFFFu, mine.l[i], 2); }
             if (lane == 0) finish_instr(v, packed, (int)(se >> 62), se & ((1ull << 62) - 1), mine, b, c, NO_SLOT);
+        } else if (working == nwarps && !(warp < working && first)) {
+            // no spare warp in this level: the warps that are not finishing prefetch while the finishers work
+            narrow_prefetch(v, l, l1, warp, nwarps, lane);
         }
         __syncthreads();
     }
@@ -769,6 +792,12 @@ int32_t zkpor_program_tail_info(zkpor_program *prog, uint64_t out3[3]) {
     ZK_REQUIRE(prog && out3, "program_tail_info: null argument");
     out3[0] = out3[1] = out3[2] = 0;
     if (prog->tail_step >= 0) { const zk::Step &t = prog->steps[(size_t)prog->tail_step]; out3[0] = t.b - t.a; out3[1] = prog->n_tail_wires; out3[2] = prog->tail_after; }
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_program_r1cs(zkpor_program *prog, zkpor_r1cs **out) {
+    ZK_REQUIRE(prog && out, "program_r1cs: null argument");
+    *out = prog->cs;
     return ZKPOR_OK;
 }
 
