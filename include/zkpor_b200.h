@@ -336,6 +336,50 @@ int32_t zkpor_tree_level(zkpor_ctx *ctx, zkpor_tree *t, uint32_t level, void **o
 int32_t zkpor_g1_decode_batch(zkpor_ctx *ctx, const void *in_bytes, uint64_t n, int32_t compressed, void *out_points);
 int32_t zkpor_g2_decode_batch(zkpor_ctx *ctx, const void *in_bytes, uint64_t n, int32_t compressed, void *out_points);
 
+/* ---- containers: the byte formats of proofs and keys (layouts in App. B.3) -------------------------
+ * gnark's marshal.go and gnark-crypto's Encoder / Decoder are out of tree (go.mod:57-60).  Everything is big-endian; WriteTo writes
+ * points compressed, WriteRawTo raw, and the decoder follows each point's flag bits, so either form is accepted on the way in; a slice
+ * is a u32 length + elements; []bool is a u32 length + ceil(len / 8) bytes (bit i % 8 of byte i / 8).  The per-point work of a 2^26 key
+ * (a square root per compressed point) runs on the GPU over the byte ranges of the caller's file buffer.  The r1cs container (CBOR +
+ * intcomp) is not read here: gnark parses it and the shim hands over the flat program (zkpor_program_upload). */
+int32_t zkpor_g1_encode_batch(zkpor_ctx *ctx, const void *points, uint64_t n, int32_t compressed, void *out_bytes);
+int32_t zkpor_g2_encode_batch(zkpor_ctx *ctx, const void *points, uint64_t n, int32_t compressed, void *out_bytes);
+/* groth16.Proof.ReadFrom (src/verifier/main.go:208-216): compressed or raw bytes -> the raw layout zkpor_groth16_verify takes
+ * (Ar 64 | Bs 128 | Krs 64 | u32 nbCommitments | Commitments 64 each | CommitmentPok 64).  *out_len: capacity in, length out. */
+int32_t zkpor_proof_decode(zkpor_ctx *ctx, const uint8_t *in, uint64_t in_len, uint8_t *out_raw, uint32_t *out_len, uint64_t *consumed);
+/* Proof.WriteTo (compressed != 0: 196 bytes with one commitment) / WriteRawTo (src/prover/prover/prover.go:201) from either form */
+int32_t zkpor_proof_encode(zkpor_ctx *ctx, const uint8_t *proof, uint32_t proof_len, int32_t compressed, uint8_t *out, uint32_t *out_len);
+/* groth16.VerifyingKey as host data (points = affine Montgomery memory images, as zkpor_vk_desc points at them) */
+typedef struct {
+    uint8_t g1_alpha[64], g1_beta[64], g1_delta[64];
+    uint8_t g2_beta[128], g2_gamma[128], g2_delta[128];
+    uint8_t g2_ped_g[128], g2_ped_g_root_sigma_neg[128];   /* vk.CommitmentKey, valid when n_commitments = 1 */
+    uint64_t n_k;                                          /* len(vk.G1.K) */
+    uint64_t n_commitments;                                /* len(vk.PublicAndCommitmentCommitted): 0 or 1 */
+    uint64_t n_public_committed;                           /* len(vk.PublicAndCommitmentCommitted[0]) */
+} zkpor_vk_host;
+/* vk.ReadFrom (src/prover/prover/prover.go:358-362, src/verifier/main.go:33-34): alpha1 beta1 beta2 gamma2 delta1 delta2 | K slice |
+ * PublicAndCommitmentCommitted | Pedersen vk -- 524 bytes for the reference circuits (README.md:54,57).  k_points receives vk.G1.K. */
+int32_t zkpor_vk_decode(zkpor_ctx *ctx, const uint8_t *in, uint64_t in_len, zkpor_vk_host *out, void *k_points, uint64_t k_cap,
+                        uint64_t *public_committed, uint64_t pc_cap, uint64_t *consumed);
+/* vk.WriteTo (raw = 0; src/keygen/main.go:46-62) / WriteRawTo.  out may be NULL to ask for the length. */
+int32_t zkpor_vk_encode(zkpor_ctx *ctx, const zkpor_vk_host *vk, const void *k_points, const uint64_t *public_committed, int32_t raw,
+                        uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+/* what a proving-key file does not hold and the resident key needs, from the constraint system */
+typedef struct {
+    uint64_t n_public;                   /* r1cs.GetNbPublicVariables(), includes the ONE wire */
+    const uint64_t *private_committed;   /* CommitmentInfo[0].PrivateCommitted, ascending */
+    uint64_t n_committed;
+    uint64_t commitment_index;           /* CommitmentInfo[0].CommitmentIndex as a wire id */
+} zkpor_pk_cs_info;
+/* pk.ReadFrom / UnsafeReadFrom (src/prover/prover/prover.go:342-346) straight into HBM: fft.Domain header | alpha1 beta1 delta1 |
+ * A[] B[] Z[] K[] | beta2 delta2 | B2[] | nbWires NbInfinityA NbInfinityB InfinityA[] InfinityB[] | u32 nbCommitmentKeys | Basis[]
+ * BasisExpSigma[].  `in` is the file's bytes in host memory (a 12 GB mmap is fine: each array is staged and decoded in one launch).
+ * Points are checked to be on the curve, not in the subgroup (UnsafeReadFrom's contract; G1 has cofactor 1). */
+int32_t zkpor_pk_read(zkpor_ctx *ctx, const uint8_t *in, uint64_t in_len, const zkpor_pk_cs_info *info, zkpor_pk **out, uint64_t *consumed);
+/* pk.WriteTo (raw = 0; src/keygen/main.go:46-62) / WriteRawTo from the resident key.  out may be NULL to ask for the length. */
+int32_t zkpor_pk_write(zkpor_ctx *ctx, zkpor_pk *pk, int32_t raw, uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+
 /* ---- groth16.Setup building blocks (src/keygen/main.go:42) -------------------------------
  * curve.BatchScalarMultiplicationG1/G2: out[i] = scalars[i] * base (affine, host or device). */
 int32_t zkpor_g1_fixed_base_batch(zkpor_ctx *ctx, const void *base_affine64, const void *scalars, uint64_t n, uint32_t flags, void *out_points);

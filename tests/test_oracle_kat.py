@@ -193,3 +193,26 @@ def test_oracle_verify_accepts_and_rejects():
     assert not g16.verify(vk, proof, [(pub[0] + 1) % R] + list(pub[1:]))
     bad = dict(proof); bad["CommitmentPok"] = pt_add(proof["CommitmentPok"], G1_GEN)
     assert not g16.verify(vk, bad, pub)
+
+
+def test_container_sizes_match_the_reference_key_files():
+    """The reference's keygen writes verifying keys of exactly 524 bytes for both tiers (README.md:54,57): one public input and one
+    commitment -> K has three entries.  The oracle's restatement of VerifyingKey.WriteTo reproduces that size; the proof containers have
+    the sizes SURVEY.md App. B.3 derives (388 raw, 196 compressed)."""
+    import containers as ct
+    import groth16 as g16
+    cs = g16.synth_r1cs(12, 6, 3)
+    pk, vk = g16.setup(cs, g16.toxic_from_seed(4))
+    assert len(vk["K"]) == 3
+    b = ct.vk_bytes(vk)
+    assert len(b) == 524 and len(ct.vk_bytes(vk, raw=True)) == 524 + 3 * 32 + 3 * 64 + 3 * 32 + 2 * 64
+    back, used = ct.vk_from_bytes(b)
+    assert used == 524 and back["K"] == vk["K"] and back["delta2"] == vk["delta2"] and back["ped_g_root_sigma_neg"] == vk["ped_g_root_sigma_neg"]
+    pub, sec = g16.synth_inputs(cs, 5)
+    proof, _ = g16.prove(cs, pk, pub, sec, 7, 9)
+    raw, comp = ct.proof_bytes(proof, raw=True), ct.proof_bytes(proof)
+    assert raw == g16.proof_raw_bytes(proof) and len(raw) == 388 and len(comp) == 196
+    assert ct.proof_from_bytes(comp)[0] == ct.proof_from_bytes(raw)[0] == proof
+    # the proving key: both encodings parse back to the same arrays, and the header names the domain
+    kb = ct.pk_bytes(pk)
+    assert int.from_bytes(kb[:8], "big") == pk["domain"].n and len(ct.pk_bytes(pk, raw=True)) > len(kb)

@@ -432,6 +432,69 @@ class PkDesc(C.Structure):
                 ("private_committed", C.c_void_p), ("commitment_index", C.c_uint64)]
 
 
+class PkCsInfo(C.Structure):
+    _fields_ = [("n_public", C.c_uint64), ("private_committed", C.c_void_p), ("n_committed", C.c_uint64), ("commitment_index", C.c_uint64)]
+
+
+class VkHost(C.Structure):
+    _fields_ = [("g1_alpha", C.c_uint8 * 64), ("g1_beta", C.c_uint8 * 64), ("g1_delta", C.c_uint8 * 64),
+                ("g2_beta", C.c_uint8 * 128), ("g2_gamma", C.c_uint8 * 128), ("g2_delta", C.c_uint8 * 128),
+                ("g2_ped_g", C.c_uint8 * 128), ("g2_ped_g_root_sigma_neg", C.c_uint8 * 128),
+                ("n_k", C.c_uint64), ("n_commitments", C.c_uint64), ("n_public_committed", C.c_uint64)]
+
+
+_VK_POINTS = ("g1_alpha", "g1_beta", "g1_delta", "g2_beta", "g2_gamma", "g2_delta", "g2_ped_g", "g2_ped_g_root_sigma_neg")
+
+
+def proof_decode(ctx: Context, data: bytes) -> bytes:
+    """groth16.Proof.ReadFrom (verifier/main.go:208-216): compressed or raw bytes -> the raw layout the verify calls take"""
+    src = np.frombuffer(data, dtype=np.uint8)
+    out = np.zeros(260 + 64 * 17, dtype=np.uint8)
+    n, used = C.c_uint32(out.size), C.c_uint64(0)
+    _check(lib().zkpor_proof_decode(ctx._h, _ptr(src), C.c_uint64(src.size), _ptr(out), C.byref(n), C.byref(used)))
+    return out[:n.value].tobytes()
+
+
+def proof_encode(ctx: Context, data: bytes, compressed: bool = True) -> bytes:
+    """Proof.WriteTo (compressed) / WriteRawTo from either form"""
+    src = np.frombuffer(data, dtype=np.uint8)
+    out = np.zeros(260 + 64 * 17, dtype=np.uint8)
+    n = C.c_uint32(out.size)
+    _check(lib().zkpor_proof_encode(ctx._h, _ptr(src), C.c_uint32(src.size), C.c_int32(1 if compressed else 0), _ptr(out), C.byref(n)))
+    return out[:n.value].tobytes()
+
+
+def vk_decode(ctx: Context, data: bytes) -> dict:
+    """vk.ReadFrom (prover.go:358-362, verifier/main.go:33-34) -> the dict the verify calls take (points as uint64 arrays)"""
+    src = np.frombuffer(data, dtype=np.uint8)
+    vk = VkHost()
+    k = np.zeros((64, 8), dtype=np.uint64)
+    pc = np.zeros(64, dtype=np.uint64)
+    used = C.c_uint64(0)
+    _check(lib().zkpor_vk_decode(ctx._h, _ptr(src), C.c_uint64(src.size), C.byref(vk), _ptr(k), C.c_uint64(k.shape[0]), _ptr(pc), C.c_uint64(pc.size), C.byref(used)))
+    out = {nm: np.frombuffer(bytes(getattr(vk, nm)), dtype=np.uint64).copy() for nm in _VK_POINTS}
+    out.update(g1_k=k[:vk.n_k].copy(), n_commitments=int(vk.n_commitments), public_committed=pc[:vk.n_public_committed].copy(), bytes_consumed=used.value)
+    return out
+
+
+def vk_encode(ctx: Context, vk: dict, raw: bool = False) -> bytes:
+    """vk.WriteTo (keygen/main.go:46-62) / WriteRawTo"""
+    h = VkHost()
+    for nm in _VK_POINTS:
+        if nm in vk and vk[nm] is not None:
+            b = np.ascontiguousarray(vk[nm], dtype=np.uint64).tobytes()
+            C.memmove(getattr(h, nm), b, len(b))
+    k = np.ascontiguousarray(vk["g1_k"], dtype=np.uint64).reshape(-1, 8)
+    pc = np.ascontiguousarray(vk.get("public_committed", []), dtype=np.uint64)
+    h.n_k, h.n_commitments, h.n_public_committed = k.shape[0], int(vk.get("n_commitments", 0)), pc.size
+    n = C.c_uint64(0)
+    args = (ctx._h, C.byref(h), _ptr(k), _ptr(pc) if pc.size else None, C.c_int32(1 if raw else 0))
+    _check(lib().zkpor_vk_encode(*args, None, C.c_uint64(0), C.byref(n)))
+    out = np.zeros(n.value, dtype=np.uint8)
+    _check(lib().zkpor_vk_encode(*args, _ptr(out), C.c_uint64(out.size), C.byref(n)))
+    return out.tobytes()
+
+
 class ProvingKey:
     """groth16.ProvingKey resident in HBM (what pk.UnsafeReadFrom fills at prover.go:342-346).  Arrays are numpy
     uint64 in gnark memory layout, or device pointers / tensors for the point arrays."""
@@ -474,6 +537,28 @@ class ProvingKey:
         self.log_n, self.n_z = log_n, n_z
         self._h = C.c_void_p()
         _check((lib().zkpor_pk_upload_shard if shard else lib().zkpor_pk_upload)(ctx._h, C.byref(d), C.byref(self._h)))
+
+    @classmethod
+    def read(cls, ctx: Context, file_bytes, n_public: int, private_committed=None, commitment_index: int = 0) -> "ProvingKey":
+        """pk.ReadFrom / UnsafeReadFrom (prover.go:342-346): the key file's bytes (compressed or raw) decoded straight into HBM.
+        n_public, private_committed and commitment_index come from the constraint system (zkpor_pk_cs_info)."""
+        buf = np.frombuffer(file_bytes, dtype=np.uint8) if not isinstance(file_bytes, np.ndarray) else file_bytes
+        pc = np.ascontiguousarray(private_committed if private_committed is not None else [], dtype=np.uint64)
+        info = PkCsInfo(n_public, _ptr(pc) if pc.size else None, pc.size, commitment_index)
+        self = cls.__new__(cls)
+        self.ctx, self._h, self.points, self.has_commitment = ctx, C.c_void_p(), {}, pc.size > 0
+        used = C.c_uint64(0)
+        _check(lib().zkpor_pk_read(ctx._h, _ptr(buf), C.c_uint64(buf.size), C.byref(info), C.byref(self._h), C.byref(used)))
+        self.bytes_consumed = used.value
+        return self
+
+    def write(self, raw: bool = False) -> bytes:
+        """pk.WriteTo (compressed) / WriteRawTo from the resident key (keygen/main.go:46-62)"""
+        n = C.c_uint64(0)
+        _check(lib().zkpor_pk_write(self.ctx._h, self._h, C.c_int32(1 if raw else 0), None, C.c_uint64(0), C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint8)
+        _check(lib().zkpor_pk_write(self.ctx._h, self._h, C.c_int32(1 if raw else 0), _ptr(out), C.c_uint64(out.size), C.byref(n)))
+        return out.tobytes()
 
     def shard_info(self) -> dict:
         out = (C.c_uint64 * 8)()
