@@ -123,3 +123,50 @@ func (c *Ctx) VerifyProof(root []byte, key uint32, proof [][]byte, leaf []byte, 
 }
 
 func (t *FixedDepthMerkleTree) Close() { C.zkpor_tree_free(t.ctx.h, t.h); t.h = nil }
+
+// ---- one tree over the GPUs of a group, and the witness service's batch loop ------------------------------------------------------------
+
+// ShardRange is the key range this context's rank owns when the tree is built across a group (zkpor_ctx_create_multi / comm_init).
+func (t *FixedDepthMerkleTree) ShardRange() (first, count uint64, subtreeLevel uint32) {
+	var f, n C.uint64_t
+	var l C.uint32_t
+	C.zkpor_tree_shard_range(t.ctx.h, t.h, &f, &n, &l)
+	return uint64(f), uint64(n), uint32(l)
+}
+
+// BuildSharded is Build() as a collective: every rank has set the leaves of its own range; subtrees per rank, all-gather of the
+// subtree roots, top levels everywhere (SURVEY.md 8(e)).  Call it from one OS-locked goroutine per rank.
+func (t *FixedDepthMerkleTree) BuildSharded() error {
+	if rc := C.zkpor_tree_build_sharded(t.ctx.h, t.h); rc != 0 {
+		return lastErr()
+	}
+	return nil
+}
+
+// CexState is what the witness loop carries from batch to batch (src/witness/witness/witness.go:144-206).
+type CexState struct {
+	BasePrices     []uint64 // utils.AssetCounts
+	TierRatioElems []byte   // AssetCounts x 18 x 32: ConvertTierRatiosToBytes of the three ratio tables, big-endian, left-padded
+	Totals         []uint64 // AssetCounts x 5
+}
+
+// WitnessBatches replaces the serial main loop for all batches of one tier: flat = the accounts' PaddingAccountAssets rows in batch
+// order, indices = their account indices.  Returns the CEX totals before every batch (+ the final ones), the n+1 CEX commitments
+// (Before of batch b = row b, After = row b+1) and the n batch commitments; GetProofs serves the account proofs.
+func (c *Ctx) WitnessBatches(st *CexState, root []byte, flat []uint64, indices []uint32, tier, opsPerBatch int) (totals []uint64, cexCm, batchCm []byte, err error) {
+	n := len(indices)
+	nb := n / opsPerBatch
+	var d C.zkpor_cex_desc
+	d.n_assets = C.uint32_t(len(st.BasePrices))
+	d.base_prices = (*C.uint64_t)(unsafe.Pointer(&st.BasePrices[0]))
+	d.tier_ratio_elems = unsafe.Pointer(&st.TierRatioElems[0])
+	d.initial_totals = (*C.uint64_t)(unsafe.Pointer(&st.Totals[0]))
+	totals = make([]uint64, (nb+1)*len(st.BasePrices)*5)
+	cexCm, batchCm = make([]byte, (nb+1)*32), make([]byte, nb*32)
+	if rc := C.zkpor_witness_batches(c.h, &d, (*C.uint8_t)(unsafe.Pointer(&root[0])), unsafe.Pointer(&flat[0]), (*C.uint32_t)(unsafe.Pointer(&indices[0])),
+		C.uint64_t(n), C.uint32_t(tier), C.uint32_t(opsPerBatch), (*C.uint64_t)(unsafe.Pointer(&totals[0])), unsafe.Pointer(&cexCm[0]), unsafe.Pointer(&batchCm[0])); rc != 0 {
+		return nil, nil, nil, lastErr()
+	}
+	copy(st.Totals, totals[nb*len(st.BasePrices)*5:]) // the next tier starts from here
+	return totals, cexCm, batchCm, nil
+}

@@ -328,6 +328,40 @@ int32_t zkpor_tree_get_proofs(zkpor_ctx *ctx, zkpor_tree *t, const uint32_t *key
 /* device pointer of level `level` (0 = leaves) and its length in nodes, for multi-GPU subtree exchange */
 int32_t zkpor_tree_level(zkpor_ctx *ctx, zkpor_tree *t, uint32_t level, void **out_dev_ptr, uint64_t *out_len);
 
+/* One tree over the GPUs of a group (contexts joined as for the sharded proof): rank g owns the leaves
+ * [g << k, (g + 1) << k), k = the smallest level with world << k >= capacity.  Every rank creates the tree with the same depth, nil leaf
+ * and capacity and sets only the leaves of its own range (zkpor_tree_shard_range); zkpor_tree_build_sharded (collective) builds the
+ * subtrees, all-gathers the N subtree roots (32 B each) and finishes the top levels on every rank, so every rank has the root.  The
+ * proofs of a key are served by the rank that owns it. */
+int32_t zkpor_tree_shard_range(zkpor_ctx *ctx, zkpor_tree *t, uint64_t *out_first_key, uint64_t *out_count, uint32_t *out_subtree_level);
+int32_t zkpor_tree_build_sharded(zkpor_ctx *ctx, zkpor_tree *t);
+
+/* ---- witness batches -------------------------------------------------------------------------------------
+ * Replaces the serial main loop of the witness service, src/witness/witness/witness.go:144-206, for all batches of one asset tier at
+ * once: the running CEX totals that fillCreateUserOp accumulates account by account (:319-340) become per-batch sums + one scan, the
+ * two 10 000-element Poseidon sponges per batch (:159-166, :176-183; the "after" state of a batch is the "before" state of the next)
+ * become n_batches + 1 independent hashes, and the batch commitments (:193-198) one more batch of 5-input hashes.  The account proofs of
+ * a batch are zkpor_tree_get_proofs on its account indices.  Host logic that stays in Go: gob + s2 serialisation and the DB writer. */
+typedef struct {
+    uint32_t n_assets;               /* utils.AssetCounts = 500 reserved CEX assets                                                 */
+    const uint64_t *base_prices;     /* n_assets: CexAssetInfo.BasePrice                                                            */
+    const void *tier_ratio_elems;    /* n_assets x 18 x 32 B big-endian: ConvertTierRatiosToBytes of Loan, Margin, PortfolioMargin
+                                        ratios (src/utils/utils.go:26-51) -- static across batches                                   */
+    const uint64_t *initial_totals;  /* n_assets x 5: TotalEquity, TotalDebt, LoanCollateral, MarginCollateral, PortfolioMargin-
+                                        Collateral before the first batch                                                            */
+} zkpor_cex_desc;
+/* flat_assets = n_accounts x tier*6 u64 (the PaddingAccountAssets layout zkpor_account_leaves takes), accounts in batch order;
+ * account_indices = their tree keys; n_accounts must be a multiple of ops_per_batch (the service pads the last batch,
+ * src/witness/main.go:71-83).  With n_batches = n_accounts / ops_per_batch:
+ *   out_totals            (n_batches + 1) x n_assets x 5 u64: the CEX totals before batch b (row n_batches: after the last one)
+ *   out_cex_commitments   (n_batches + 1) x 32 B: BeforeCEXAssetsCommitment of batch b = row b, AfterCEXAssetsCommitment = row b + 1
+ *   out_batch_commitments n_batches x 32 B: BatchCommitment
+ * Outputs may be host or device pointers, or NULL.  A total that overflows 64 bits (utils.SafeAdd panics) or an asset index
+ * >= n_assets is ZKPOR_ERR_STATE. */
+int32_t zkpor_witness_batches(zkpor_ctx *ctx, const zkpor_cex_desc *cex, const uint8_t account_tree_root[32], const void *flat_assets,
+                              const uint32_t *account_indices, uint64_t n_accounts, uint32_t tier, uint32_t ops_per_batch,
+                              uint64_t *out_totals, void *out_cex_commitments, void *out_batch_commitments);
+
 /* ---- point decoding (pk.UnsafeReadFrom's square roots) -----------------------------------
  * gnark-crypto bn254 encodings (ecc/bn254/marshal.go, out of tree): compressed = 32 B (G1) / 64 B (G2, X.A1 first),
  * raw = 64 B / 128 B, big-endian, flags in the top two bits of byte 0 (00 raw, 10/11 compressed smaller/larger y,

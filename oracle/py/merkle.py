@@ -202,3 +202,33 @@ def cex_assets_commitment(cex_assets, out_lane=None) -> bytes:
     for a in full:
         elems += cex_asset_packed(a)
     return poseidon(elems, out_lane).to_bytes(32, "big")
+
+
+# ----------------------------------------------------------------------------- witness batches
+def witness_batches(cex_assets, root: bytes, accounts, ops_per_batch: int, out_lane=None):
+    """The witness service's main loop, src/witness/witness/witness.go:144-206, restated as it is written: batch after batch, the CEX
+    state is hashed (BeforeCEXAssetsCommitment), every account's assets are added to the running totals (fillCreateUserOp,
+    :319-340), the state is hashed again (AfterCEXAssetsCommitment) and BatchCommitment = Poseidon(root, before, after, min, max)
+    (:185-198; a zero index is []byte{0}, the element 0).
+    cex_assets: list of dicts as cex_asset_packed takes (mutated copies are returned); accounts: list of (account_index, assets) with
+    assets = [(index, equity, debt, loan, margin, pm)], a multiple of ops_per_batch of them.
+    Returns [(before_totals, before_commitment, after_commitment, batch_commitment)] per batch and the final totals."""
+    assert len(accounts) % ops_per_batch == 0
+    state = [dict(a) for a in cex_assets]
+    out = []
+    for b in range(len(accounts) // ops_per_batch):
+        before_totals = [(a["total_equity"], a["total_debt"], a["loan"], a["margin"], a["pm"]) for a in state]
+        before = cex_assets_commitment(state, out_lane)
+        batch = accounts[b * ops_per_batch:(b + 1) * ops_per_batch]
+        for _, assets in batch:
+            for (idx, eq, debt, loan, margin, pm) in assets:
+                a = state[idx]
+                for k, v in (("total_equity", eq), ("total_debt", debt), ("loan", loan), ("margin", margin), ("pm", pm)):
+                    a[k] += v
+                    assert a[k] < (1 << 64), "utils.SafeAdd: overflow"
+        after = cex_assets_commitment(state, out_lane)
+        lo, hi = batch[0][0], batch[-1][0]
+        bc = poseidon_bytes([root, before, after, lo.to_bytes(max(1, (lo.bit_length() + 7) // 8), "big"),
+                             hi.to_bytes(max(1, (hi.bit_length() + 7) // 8), "big")], out_lane)
+        out.append((before_totals, before, after, bc))
+    return out, [(a["total_equity"], a["total_debt"], a["loan"], a["margin"], a["pm"]) for a in state]

@@ -211,3 +211,105 @@ def test_cex_assets_commitment_10000_elements(ctx):
     ctx.set_poseidon_out_lane(1); orc.poseidon_set_out_lane(1)
     # batch commitment = PoseidonBytes(root, before, after, min, max) with the []byte{0} quirk for a zero index (witness.go:185-198)
     assert ctx.poseidon_bytes(got, got, want, b"\x00", (1379).to_bytes(2, "big")) == ps.poseidon_bytes([got, got, want, b"\x00", (1379).to_bytes(2, "big")], 1)
+
+
+def _fast_cex_commitment(state, out_lane=None):
+    """merkle.cex_assets_commitment with the 834 permutations done by the C oracle (the Python loop takes seconds per hash)"""
+    empty = dict(total_equity=0, total_debt=0, base_price=0, loan=0, margin=0, pm=0, loan_ratios=[(0, 0)] * 12, margin_ratios=[(0, 0)] * 12, pm_ratios=[(0, 0)] * 12)
+    elems = []
+    for a in list(state) + [empty] * (merkle.ASSET_COUNTS - len(state)):
+        elems += merkle.cex_asset_packed(a)
+    return orc.fr_unmont(orc.poseidon_hash(orc.fr_mont(elems)))[0].to_bytes(32, "big")
+
+
+def test_witness_batches_vs_oracle(ctx, monkeypatch):
+    """zkpor_witness_batches against the reference's serial loop as restated in oracle/py/merkle.py (witness.go:144-206): running CEX
+    totals, before / after commitments of every batch, batch commitments -- including a first batch that starts at account index 0."""
+    rng = SplitMix64(77)
+    n_assets, tier, ops, nb = merkle.ASSET_COUNTS, 50, 6, 4
+    cex = []
+    for i in range(9):
+        tiers = [(int(rng.next() % (1 << 100)), int(rng.next() % 101)) for _ in range(merkle.TIER_COUNT)]
+        cex.append(dict(total_equity=rng.next() >> 8, total_debt=rng.next() >> 8, base_price=rng.next(), loan=rng.next() >> 8, margin=rng.next() >> 8, pm=rng.next() >> 8,
+                        loan_ratios=tiers, margin_ratios=tiers[::-1], pm_ratios=tiers))
+    accounts = []
+    for j in range(ops * nb):
+        k = 1 + rng.next() % 5
+        idxs = sorted({int(rng.next() % 9) for _ in range(k)})
+        accounts.append((j, [(i, rng.next() >> 12, rng.next() >> 12, rng.next() >> 12, rng.next() >> 12, rng.next() >> 12) for i in idxs]))
+    root = (0x1234567890ABCDEF << 64 | 12345).to_bytes(32, "big")
+    monkeypatch.setattr(merkle, "cex_assets_commitment", _fast_cex_commitment)
+    want, final = merkle.witness_batches(cex, root, accounts, ops)
+    # inputs as the Go side holds them
+    base_prices = np.zeros(n_assets, dtype=np.uint64); totals0 = np.zeros((n_assets, 5), dtype=np.uint64)
+    tier_elems = np.zeros((n_assets, 18, 32), dtype=np.uint8)
+    for i, a in enumerate(cex):
+        base_prices[i] = a["base_price"]
+        totals0[i] = [a["total_equity"], a["total_debt"], a["loan"], a["margin"], a["pm"]]
+        packed = merkle.tier_ratios_packed(a["loan_ratios"]) + merkle.tier_ratios_packed(a["margin_ratios"]) + merkle.tier_ratios_packed(a["pm_ratios"])
+        tier_elems[i] = orc.be32_array(packed)
+    flat = np.array([merkle.padding_account_assets(assets) for _, assets in accounts], dtype=np.uint64)
+    assert flat.shape == (ops * nb, tier * 6)
+    idx = np.array([j for j, _ in accounts], dtype=np.uint32)
+    totals, cm, bc = zk.witness_batches(ctx, base_prices=base_prices, tier_ratio_elems=tier_elems, initial_totals=totals0, root=root, flat_assets=flat,
+                                        account_indices=idx, tier=tier, ops_per_batch=ops)
+    for b, (before_totals, before, after, batch_cm) in enumerate(want):
+        assert [tuple(int(x) for x in row) for row in totals[b][:9]] == before_totals[:9]
+        assert cm[b].tobytes() == before and cm[b + 1].tobytes() == after and bc[b].tobytes() == batch_cm
+    assert [tuple(int(x) for x in row) for row in totals[nb][:9]] == final[:9]
+    # device-resident inputs, outputs not wanted: same commitments
+    import torch
+    tf = torch.from_numpy(flat.view(np.int64)).cuda()
+    _, cm2, _ = zk.witness_batches(ctx, base_prices=base_prices, tier_ratio_elems=tier_elems, initial_totals=totals0, root=root, flat_assets=tf,
+                                   account_indices=idx, tier=tier, ops_per_batch=ops)
+    assert np.array_equal(cm, cm2)
+    # an overflowing total and an asset index beyond the table fail loudly (utils.SafeAdd panics)
+    big = totals0.copy(); big[0, 0] = (1 << 64) - 1
+    bad_flat = flat.copy(); bad_flat[0, 0] = 0; bad_flat[0, 1] = 5
+    with pytest.raises(zk.ZkporError, match="overflows"):
+        zk.witness_batches(ctx, base_prices=base_prices, tier_ratio_elems=tier_elems, initial_totals=big, root=root, flat_assets=bad_flat, account_indices=idx, tier=tier, ops_per_batch=ops)
+    bad_flat = flat.copy(); bad_flat[3, 0] = 501
+    with pytest.raises(zk.ZkporError, match="asset index"):
+        zk.witness_batches(ctx, base_prices=base_prices, tier_ratio_elems=tier_elems, initial_totals=totals0, root=root, flat_assets=bad_flat, account_indices=idx, tier=tier, ops_per_batch=ops)
+    with pytest.raises(zk.ZkporError, match="whole batches"):
+        zk.witness_batches(ctx, base_prices=base_prices, tier_ratio_elems=tier_elems, initial_totals=totals0, root=root, flat_assets=flat[:7], account_indices=idx[:7], tier=tier, ops_per_batch=ops)
+
+
+@pytest.mark.parametrize("world,capacity", [(2, 1000), (4, 777), (8, 5000), (4, 3)])
+def test_tree_built_across_ranks_matches_single(world, capacity):
+    """account ranges -> one subtree per GPU -> all-gather of the subtree roots -> top levels on every rank.  The group
+    is the in-process one (device ids may repeat), one host thread per rank; the root and every owner-served proof equal the single-GPU
+    tree's (FixedDepthMerkleTree.Build / GetProof, merkletree.go:192-308)."""
+    depth = 28
+    rng = SplitMix64(900 + world + capacity)
+    leaves = orc.be32_array([rng.field(R) for _ in range(capacity)])
+    nil = merkle.nil_account_hash()
+    single = zk.Context(0)
+    t1 = zk.FixedDepthMerkleTree(single, depth, nil, capacity)
+    t1.set_range(0, leaves, capacity); t1.build()
+    _, want_root = orc.merkle_build(leaves, capacity, depth, nil)
+    assert t1.root() == want_root
+    have = zk.device_count()
+    ctxs = zk.create_multi([i % have for i in range(world)])
+
+    def rank_fn(r):
+        t = zk.FixedDepthMerkleTree(ctxs[r], depth, nil, capacity)
+        first, count, level = t.shard_range()
+        if count:
+            t.set_range(first, leaves[first:first + count], count)
+        t.build_sharded()
+        keys = np.arange(first, first + count, dtype=np.uint32)[:: max(1, count // 5)] if count else np.zeros(0, dtype=np.uint32)
+        proofs = t.get_proofs(keys) if len(keys) else None
+        return t.root(), keys, proofs, (first, count, level)
+
+    res = zk.run_ranks(rank_fn, world)
+    covered = 0
+    for root, keys, proofs, (first, count, level) in res:
+        assert root == want_root
+        covered += count
+        if len(keys):
+            assert np.array_equal(proofs, t1.get_proofs(keys))
+    assert covered == capacity
+    for cx in ctxs:
+        cx.close()
+    single.close()

@@ -73,3 +73,34 @@ def test_partition_plan_covers_every_digit():
         max_top_digit = min(nb, (1 << top_raw))
         assert ((max_top_digit - 1) >> shift_top) < (1 << PART_BITS)
         assert (1 << shift_top) <= 8192
+
+
+def test_witness_batches_restatement_is_a_prefix_sum(monkeypatch):
+    """oracle/py/merkle.py witness_batches restates the reference's serial loop (witness.go:144-206).  What the GPU pipeline relies on:
+    the after-state of a batch is the before-state of the next (so n + 1 commitments serve n batches), and the totals are the initial
+    ones plus the per-batch sums."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle", "py"))
+    import merkle
+    import orc
+    from bn254 import SplitMix64
+
+    def fast(state, out_lane=None):      # the 834-permutation sponge by the C oracle
+        empty = dict(total_equity=0, total_debt=0, base_price=0, loan=0, margin=0, pm=0, loan_ratios=[(0, 0)] * 12, margin_ratios=[(0, 0)] * 12, pm_ratios=[(0, 0)] * 12)
+        elems = []
+        for a in list(state) + [empty] * (merkle.ASSET_COUNTS - len(state)):
+            elems += merkle.cex_asset_packed(a)
+        return orc.fr_unmont(orc.poseidon_hash(orc.fr_mont(elems)))[0].to_bytes(32, "big")
+
+    assert fast([]) == merkle.cex_assets_commitment([])          # the C sponge is the Python one
+    monkeypatch.setattr(merkle, "cex_assets_commitment", fast)
+    rng = SplitMix64(5)
+    cex = [dict(total_equity=10 * i, total_debt=i, base_price=7 + i, loan=0, margin=3, pm=1, loan_ratios=[(5, 50)] * 12, margin_ratios=[(6, 60)] * 12, pm_ratios=[(7, 70)] * 12)
+           for i in range(4)]
+    accounts = [(j, [(int(rng.next() % 4), 1 + j, 2, 3, 4, 5)]) for j in range(6)]
+    out, final = merkle.witness_batches(cex, bytes(32), accounts, 2)
+    assert len(out) == 3
+    for b in range(2):
+        assert out[b][2] == out[b + 1][1]                         # after(b) == before(b+1)
+    assert sum(t[0] for t in final) == sum(a["total_equity"] for a in cex) + sum(1 + j for j in range(6))
+    assert out[0][0][:4] == [(a["total_equity"], a["total_debt"], a["loan"], a["margin"], a["pm"]) for a in cex]

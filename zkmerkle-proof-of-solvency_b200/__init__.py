@@ -405,10 +405,40 @@ class FixedDepthMerkleTree:
         _check(lib().zkpor_tree_get_proofs(self.ctx._h, self._h, _ptr(k), C.c_uint64(k.size), _ptr(out)))
         return out
 
+    def shard_range(self):
+        """(first key, number of keys, subtree level) of this context's rank when the tree is built across a group of GPUs"""
+        first, count, lvl = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        _check(lib().zkpor_tree_shard_range(self.ctx._h, self._h, C.byref(first), C.byref(count), C.byref(lvl)))
+        return first.value, count.value, lvl.value
+
+    def build_sharded(self):
+        """collective Build over the context's group: subtrees per rank, all-gather of the subtree roots, top levels everywhere"""
+        _check(lib().zkpor_tree_build_sharded(self.ctx._h, self._h))
+
     def level(self, level: int):
         p, n = C.c_void_p(), C.c_uint64(0)
         _check(lib().zkpor_tree_level(self.ctx._h, self._h, C.c_uint32(level), C.byref(p), C.byref(n)))
         return p.value, n.value
+
+
+class CexDesc(C.Structure):
+    _fields_ = [("n_assets", C.c_uint32), ("base_prices", C.c_void_p), ("tier_ratio_elems", C.c_void_p), ("initial_totals", C.c_void_p)]
+
+
+def witness_batches(ctx: Context, *, base_prices, tier_ratio_elems, initial_totals, root: bytes, flat_assets, account_indices, tier: int, ops_per_batch: int):
+    """The witness service's main loop (witness.go:144-206) for all batches of one tier: returns (totals (nb+1, n_assets, 5) uint64,
+    cex_commitments (nb+1, 32) uint8, batch_commitments (nb, 32) uint8).  base_prices (n_assets,) uint64; tier_ratio_elems
+    (n_assets, 18, 32) uint8 big-endian; initial_totals (n_assets, 5) uint64; flat_assets (n_accounts, tier*6) uint64."""
+    bp = np.ascontiguousarray(base_prices, dtype=np.uint64); te = np.ascontiguousarray(tier_ratio_elems, dtype=np.uint8); it = np.ascontiguousarray(initial_totals, dtype=np.uint64)
+    idx = np.ascontiguousarray(account_indices, dtype=np.uint32)
+    n_assets, n = bp.size, idx.size
+    nb = n // ops_per_batch
+    d = CexDesc(n_assets, _ptr(bp), _ptr(te), _ptr(it))
+    totals = np.zeros((nb + 1, n_assets, 5), dtype=np.uint64); cm = np.zeros((nb + 1, 32), dtype=np.uint8); bc = np.zeros((nb, 32), dtype=np.uint8)
+    rt = (C.c_uint8 * 32).from_buffer_copy(root)
+    _check(lib().zkpor_witness_batches(ctx._h, C.byref(d), rt, _ptr(flat_assets), _ptr(idx), C.c_uint64(n), C.c_uint32(tier), C.c_uint32(ops_per_batch),
+                                       _ptr(totals), _ptr(cm), _ptr(bc)))
+    return totals, cm, bc
 
 
 def verify_proof(ctx: Context, root: bytes, key: int, proof, leaf: bytes, depth: int) -> bool:

@@ -11,6 +11,7 @@
 // Kernels: 2-to-1 node hash = one thread per node (t = 3 state in registers); wide hashes = 16 lanes per hash, one
 // state element per lane, MDS row-times-vector with warp shuffles.
 #include "internal.h"
+#include <algorithm>
 
 using namespace ff;
 
@@ -499,6 +500,87 @@ __global__ void k_get_leaves(TreeDev t, const uint32_t *__restrict__ keys, uint6
 
 using namespace zk;
 
+// ---- witness batches: the serial main loop of the witness service, src/witness/witness/witness.go:144-206 ----
+// The reference walks the batches one after the other: it adds every account's assets to the running CEX totals (fillCreateUserOp,
+// witness.go:319-340) and hashes the 10 000 packed elements of the CEX state before and after each batch (:159-166, :176-183) -- two
+// serial 834-permutation sponges per batch on one core.  A prefix sum is not serial: per-batch deltas (one CTA per batch), one scan
+// over the batches, then ALL states' commitments at once (16 lanes per state), then the batch commitments (:193-198).
+static const uint32_t CEX_ELEMS_PER_ASSET = 20;   // 2 packed totals + 3 x 6 packed tier-ratio pairs (src/utils/utils.go:53-88)
+static const uint32_t CEX_FIELDS = 5;             // TotalEquity, TotalDebt, LoanCollateral, MarginCollateral, PortfolioMarginCollateral
+
+// delta[b][asset][field] = sum over the accounts of batch b; flat = PaddingAccountAssets layout (index, equity, debt, loan, margin, pm per slot)
+__global__ void __launch_bounds__(256) k_batch_deltas(const uint64_t *__restrict__ flat, uint32_t tier, uint32_t ops_per_batch, uint32_t n_assets,
+                                                      uint64_t *__restrict__ delta, unsigned long long *__restrict__ err) {
+    extern __shared__ unsigned long long acc[];
+    const uint32_t nacc = n_assets * CEX_FIELDS;
+    for (uint32_t i = threadIdx.x; i < nacc; i += blockDim.x) acc[i] = 0;
+    __syncthreads();
+    const uint64_t b = blockIdx.x, slots = (uint64_t)ops_per_batch * tier;
+    const uint64_t *f0 = flat + b * slots * 6;
+    for (uint64_t sl = threadIdx.x; sl < slots; sl += blockDim.x) {
+        const uint64_t *f = f0 + sl * 6;
+        const uint64_t idx = f[0];
+        if (idx >= n_assets) { atomicCAS(err, 0ull, (2ull << 56) | (b * ops_per_batch + sl / tier)); continue; }
+#pragma unroll
+        for (uint32_t k = 0; k < CEX_FIELDS; k++) {
+            const unsigned long long v = f[1 + k];
+            if (v == 0) continue;
+            const unsigned long long old = atomicAdd(&acc[idx * CEX_FIELDS + k], v);
+            if (old + v < old) atomicCAS(err, 0ull, (1ull << 56) | b);            // utils.SafeAdd panics on overflow
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nacc; i += blockDim.x) delta[b * nacc + i] = acc[i];
+}
+// totals[0] = initial, totals[b + 1] = totals[b] + delta[b]   (in place: totals[1..] holds the deltas on entry)
+__global__ void k_totals_scan(uint64_t *__restrict__ totals, uint32_t nacc, uint64_t n_batches, unsigned long long *__restrict__ err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nacc) return;
+    uint64_t run = totals[i];
+    for (uint64_t b = 0; b < n_batches; b++) {
+        const uint64_t d = totals[(b + 1) * nacc + i], next = run + d;
+        if (next < run) atomicCAS(err, 0ull, (1ull << 56) | b);
+        totals[(b + 1) * nacc + i] = run = next;
+    }
+}
+__device__ __forceinline__ Fr pack3_mont(uint64_t a, uint64_t b, uint64_t c) {   // a*2^128 + b*2^64 + c
+    Fr v = Fr::zero();
+    v.l[0] = (uint32_t)c; v.l[1] = (uint32_t)(c >> 32); v.l[2] = (uint32_t)b; v.l[3] = (uint32_t)(b >> 32); v.l[4] = (uint32_t)a; v.l[5] = (uint32_t)(a >> 32);
+    return Fr::to_mont(v);
+}
+// commitment of CEX state g (g = 0 .. n_batches): Poseidon over n_assets x 20 elements, 16 lanes per state
+__global__ void __launch_bounds__(128) k_cex_commitments(const uint64_t *__restrict__ totals, const uint64_t *__restrict__ base_price,
+                                                         const uint8_t *__restrict__ tier_elems, uint32_t n_assets, uint64_t count,
+                                                         uint8_t *__restrict__ out, PoseidonTables tab, int out_lane) {
+    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int lane = threadIdx.x & 15;
+    const bool live = g < count;
+    const uint64_t *t = totals + (live ? g : count - 1) * n_assets * CEX_FIELDS;
+    const Fr h = group_hash([&](uint32_t k) {
+        const uint32_t a = k / CEX_ELEMS_PER_ASSET, e = k - a * CEX_ELEMS_PER_ASSET;
+        if (e == 0) return pack3_mont(t[a * CEX_FIELDS], t[a * CEX_FIELDS + 1], base_price[a]);
+        if (e == 1) return pack3_mont(t[a * CEX_FIELDS + 2], t[a * CEX_FIELDS + 3], t[a * CEX_FIELDS + 4]);
+        return load_be_mont(tier_elems + ((size_t)a * (CEX_ELEMS_PER_ASSET - 2) + (e - 2)) * 32);
+    }, n_assets * CEX_ELEMS_PER_ASSET, lane, tab, out_lane);
+    if (live && lane == 0) store_be_plain(out + g * 32, h);
+}
+// BatchCommitment = Poseidon(AccountTreeRoot, Before, After, MinAccountIndex, MaxAccountIndex)   (witness.go:193-198)
+__global__ void __launch_bounds__(128) k_batch_commitments(const uint8_t *__restrict__ root, const uint8_t *__restrict__ cex_cm,
+                                                           const uint32_t *__restrict__ account_index, uint32_t ops_per_batch, uint64_t n_batches,
+                                                           uint8_t *__restrict__ out, PoseidonTables tab, int out_lane) {
+    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int lane = threadIdx.x & 15;
+    const bool live = g < n_batches;
+    const uint64_t b = live ? g : n_batches - 1;
+    const Fr h = group_hash([&](uint32_t k) {
+        if (k == 0) return load_be_mont(root);
+        if (k == 1) return load_be_mont(cex_cm + b * 32);
+        if (k == 2) return load_be_mont(cex_cm + (b + 1) * 32);
+        return Fr::from_u64(account_index[b * ops_per_batch + (k == 3 ? 0 : ops_per_batch - 1)]);
+    }, 5, lane, tab, out_lane);
+    if (live && lane == 0) store_be_plain(out + g * 32, h);
+}
+
 struct zkpor_tree {
     uint32_t depth = 0;
     uint64_t capacity = 0;
@@ -728,6 +810,114 @@ int32_t zkpor_tree_level(zkpor_ctx *ctx, zkpor_tree *t, uint32_t level, void **o
     ZK_REQUIRE(ctx && t && out_dev_ptr && out_len, "tree_level: null argument");
     ZK_REQUIRE(level <= t->depth, "tree_level: level out of range");
     *out_dev_ptr = t->node[level]; *out_len = t->len[level];
+    return ZKPOR_OK;
+}
+
+
+// ---- one tree over the GPUs of a group: rank g owns the leaves [g << k, (g + 1) << k), builds the subtree above them,
+// the N subtree roots are all-gathered (32 B each) and every rank finishes the top levels.  Every rank creates the tree with the same
+// depth / nil leaf / capacity and sets only leaves of its own range; proofs of a key are served by the rank that owns it (the siblings
+// below level k live there; those at and above level k are on every rank).
+int32_t zkpor_tree_shard_range(zkpor_ctx *ctx, zkpor_tree *t, uint64_t *out_first_key, uint64_t *out_count, uint32_t *out_subtree_level) {
+    ZK_REQUIRE(ctx && t && out_first_key && out_count, "tree_shard_range: null argument");
+    int rank, world; comm_info(ctx, &rank, &world);
+    uint32_t k = 0;
+    while (k < t->depth && ((uint64_t)world << k) < t->capacity) k++;
+    const uint64_t first = (uint64_t)rank << k;
+    *out_first_key = first < t->capacity ? first : t->capacity;
+    *out_count = first < t->capacity ? std::min<uint64_t>((uint64_t)1 << k, t->capacity - first) : 0;
+    if (out_subtree_level) *out_subtree_level = k;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_tree_build_sharded(zkpor_ctx *ctx, zkpor_tree *t) {
+    ZK_REQUIRE(ctx && t, "tree_build_sharded: null argument");
+    int rank, world; comm_info(ctx, &rank, &world);
+    if (world == 1) return zkpor_tree_build(ctx, t);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    stages_reset(ctx);
+    PoseidonTables tab; ZK_TRY(get_tables(ctx, &tab));
+    uint64_t first, count; uint32_t k;
+    ZK_TRY(zkpor_tree_shard_range(ctx, t, &first, &count, &k));
+    stage_begin(ctx, ST_POSEIDON);
+    auto level = [&](uint32_t l) -> int32_t {
+        ZK_LAUNCH(ctx, k_merkle_level, grid_for(t->len[l], 128), 128, 0, (const uint8_t *)t->node[l - 1], (const uint8_t *)t->dirty[l - 1],
+                  t->len[l - 1], t->node[l], t->dirty[l], t->len[l], (const uint8_t *)(t->nil + 32 * (l - 1)), (const uint8_t *)(t->nil + 32 * l), tab, t->out_lane);
+        return ZKPOR_OK;
+    };
+    for (uint32_t l = 1; l <= k; l++) ZK_TRY(level(l));
+    // the subtree roots meet: node[k][g] of rank g (the empty-subtree value where a rank has no leaves)
+    uint8_t mine[32], all[8 * 32];
+    ZK_REQUIRE(world <= 8, "tree_build_sharded: at most 8 ranks");
+    if ((uint64_t)rank < t->len[k]) ZK_CUDA(cudaMemcpyAsync(mine, t->node[k] + (size_t)rank * 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    else memcpy(mine, t->nil_host[k], 32);
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZK_TRY(comm_all_gather_host(ctx, mine, all, 32));
+    const uint64_t have = std::min<uint64_t>((uint64_t)world, t->len[k]);
+    ZK_CUDA(cudaMemcpyAsync(t->node[k], all, have * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(cudaMemsetAsync(t->dirty[k], 1, have, ctx->stream));
+    for (uint32_t l = k + 1; l <= t->depth; l++) ZK_TRY(level(l));
+    stage_end(ctx, ST_POSEIDON);
+    ZK_CUDA(cudaMemcpyAsync(t->root, t->node[t->depth], 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    stages_collect(ctx);
+    t->built = true;
+    return ZKPOR_OK;
+}
+
+int32_t zkpor_witness_batches(zkpor_ctx *ctx, const zkpor_cex_desc *cex, const uint8_t account_tree_root[32], const void *flat_assets,
+                              const uint32_t *account_indices, uint64_t n_accounts, uint32_t tier, uint32_t ops_per_batch,
+                              uint64_t *out_totals, void *out_cex_commitments, void *out_batch_commitments) {
+    ZK_REQUIRE(ctx && cex && account_tree_root && flat_assets && account_indices, "witness_batches: null argument");
+    ZK_REQUIRE(cex->n_assets >= 1 && cex->n_assets <= 1200 && cex->base_prices && cex->tier_ratio_elems && cex->initial_totals, "witness_batches: bad CEX description (at most 1200 assets)");
+    ZK_REQUIRE(tier >= 1 && ops_per_batch >= 1 && n_accounts > 0 && n_accounts % ops_per_batch == 0,
+               "witness_batches: the accounts must fill whole batches (the witness service pads the last one, src/witness/main.go:71-83)");
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    stages_reset(ctx);
+    PoseidonTables tab; ZK_TRY(get_tables(ctx, &tab));
+    const uint64_t nb = n_accounts / ops_per_batch;
+    const uint32_t nacc = cex->n_assets * CEX_FIELDS;
+    const void *d_flat, *d_idx;
+    stage_begin(ctx, ST_H2D);
+    ZK_TRY(to_device(ctx, flat_assets, n_accounts * (size_t)tier * 48, ctx->in_points, &d_flat));
+    ZK_TRY(to_device(ctx, account_indices, n_accounts * 4, ctx->in_scalars, &d_idx));
+    // scratch: totals (nb+1) x nacc u64 | base prices | tier elements | root | commitments (nb+1) x 32 | batch commitments nb x 32 | err
+    const size_t o_tot = 0, o_price = o_tot + (nb + 1) * (size_t)nacc * 8, o_tier = o_price + (size_t)cex->n_assets * 8,
+                 o_root = o_tier + (size_t)cex->n_assets * (CEX_ELEMS_PER_ASSET - 2) * 32, o_cm = o_root + 32, o_bc = o_cm + (nb + 1) * 32,
+                 o_err = o_bc + nb * 32, total = o_err + 16;
+    ZK_TRY(ctx->io.reserve(total));
+    uint8_t *base = ctx->io.as<uint8_t>();
+    uint64_t *d_tot = (uint64_t *)(base + o_tot);
+    unsigned long long *d_err = (unsigned long long *)(base + o_err);
+    ZK_CUDA(cudaMemcpyAsync(d_tot, cex->initial_totals, (size_t)nacc * 8, cudaMemcpyDefault, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(base + o_price, cex->base_prices, (size_t)cex->n_assets * 8, cudaMemcpyDefault, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(base + o_tier, cex->tier_ratio_elems, (size_t)cex->n_assets * (CEX_ELEMS_PER_ASSET - 2) * 32, cudaMemcpyDefault, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(base + o_root, account_tree_root, 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(cudaMemsetAsync(d_err, 0, 16, ctx->stream));
+    stage_end(ctx, ST_H2D);
+    stage_begin(ctx, ST_POSEIDON);
+    ZK_LAUNCH(ctx, k_batch_deltas, (int)nb, 256, (size_t)nacc * 8, (const uint64_t *)d_flat, tier, ops_per_batch, cex->n_assets, d_tot + nacc, d_err);
+    ZK_LAUNCH(ctx, k_totals_scan, grid_for(nacc, 128), 128, 0, d_tot, nacc, nb, d_err);
+    ZK_LAUNCH(ctx, k_cex_commitments, grid_for((nb + 1) * 16, 128), 128, 0, (const uint64_t *)d_tot, (const uint64_t *)(base + o_price), (const uint8_t *)(base + o_tier),
+              cex->n_assets, nb + 1, base + o_cm, tab, ctx->poseidon_out_lane);
+    ZK_LAUNCH(ctx, k_batch_commitments, grid_for(nb * 16, 128), 128, 0, (const uint8_t *)(base + o_root), (const uint8_t *)(base + o_cm), (const uint32_t *)d_idx,
+              ops_per_batch, nb, base + o_bc, tab, ctx->poseidon_out_lane);
+    stage_end(ctx, ST_POSEIDON);
+    unsigned long long err = 0;
+    stage_begin(ctx, ST_D2H);
+    ZK_CUDA(cudaMemcpyAsync(&err, d_err, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_totals) ZK_CUDA(cudaMemcpyAsync(out_totals, d_tot, (nb + 1) * (size_t)nacc * 8, cudaMemcpyDefault, ctx->stream));
+    if (out_cex_commitments) ZK_CUDA(cudaMemcpyAsync(out_cex_commitments, base + o_cm, (nb + 1) * 32, cudaMemcpyDefault, ctx->stream));
+    if (out_batch_commitments) ZK_CUDA(cudaMemcpyAsync(out_batch_commitments, base + o_bc, nb * 32, cudaMemcpyDefault, ctx->stream));
+    stage_end(ctx, ST_D2H);
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    stages_collect(ctx);
+    if (err) {
+        const unsigned long long where = err & ((1ull << 56) - 1);
+        if ((err >> 56) == 2) set_error("witness_batches: account #%llu holds an asset index beyond the %u CEX assets", where, cex->n_assets);
+        else set_error("witness_batches: a CEX total overflows 64 bits in batch #%llu (utils.SafeAdd)", where);
+        return ZKPOR_ERR_STATE;
+    }
     return ZKPOR_OK;
 }
 
