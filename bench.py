@@ -72,6 +72,9 @@ def parse():
     ap.add_argument("--no-parity", action="store_true", help="skip the discrete-log check of the timed proof (it costs ~1 min of host time at 2^26)")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-proof-across-N-GPUs measurement")
     ap.add_argument("--provers", type=int, default=2, help="provers per GPU (each with its own context, key and program), proving independent batches concurrently")
+    ap.add_argument("--workload", default="prove", choices=["prove", "witness"],
+                    help="prove: groth16.Prove (the headline metric); witness: the witness service's hot path on --accounts synthetic accounts (BASELINE config 5)")
+    ap.add_argument("--accounts", type=int, default=10_000_000)
     return ap.parse_args()
 
 
@@ -339,6 +342,10 @@ DTYPE = "u32 limbs (254-bit modular integers)"
 
 def main():
     args = parse()
+    if args.workload == "witness" and args.impl == "native":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import witness_bench
+        return witness_bench.main(args)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference" and rank != 0:
         return 0
