@@ -29,6 +29,7 @@ for st in $steps; do
     witness) timeout 900 python bench.py --workload witness > gpurun_out/s_witness.json 2> gpurun_out/s_witness.err; echo "witness rc=$?"; tail -c 2500 gpurun_out/s_witness.json; tail -5 gpurun_out/s_witness.err ;;
     witness_small) timeout 600 python bench.py --workload witness --accounts 400000 > gpurun_out/s_witness_small.json 2> gpurun_out/s_witness_small.err; echo "witness_small rc=$?"; tail -c 2500 gpurun_out/s_witness_small.json; tail -5 gpurun_out/s_witness_small.err ;;
     ncu_poseidon) timeout 900 ncu --set full --import-source on --clock-control none -k regex:'k_account_leaves_tpa|k_merkle_level|k_cex_commitments' --launch-skip 2 -c 6 -f -o gpurun_out/r02_poseidon python bench.py --workload witness --accounts 600000 > gpurun_out/s_ncu_poseidon.log 2>&1; echo "ncu poseidon rc=$?"; tail -3 gpurun_out/s_ncu_poseidon.log | cut -c1-300 ;;
+    ncu_accumulate) timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_accumulate --launch-skip 2 -c 2 -f -o gpurun_out/r02_accumulate python tools/ncu_traffic.py run 24 > gpurun_out/s_ncu_acc.log 2>&1; echo "ncu accumulate rc=$?"; tail -3 gpurun_out/s_ncu_acc.log | cut -c1-300 ;;
     ncu_narrow) timeout 900 ncu --set full --import-source on --clock-control none -k k_solve_narrow --launch-skip 6 -c 3 -f -o gpurun_out/r02_narrow python tools/solver_bench.py 22 96:512:9 > gpurun_out/s_ncu_narrow.log 2>&1; echo "ncu narrow rc=$?"; tail -3 gpurun_out/s_ncu_narrow.log | cut -c1-300 ;;
     *) echo "unknown step $st" ;;
   esac
