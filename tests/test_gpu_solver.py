@@ -152,3 +152,24 @@ def test_deferred_tail_gives_the_same_proof(ctx, monkeypatch):
         pk.prove_solve(prog, orc.fr_mont(bad), r, s)
     assert pk.prove_solve(prog, inst["inputs_mont"], r, s) == want
     prog.close(); plain.close(); pk.close()
+
+
+@pytest.mark.parametrize("pipe", ["0", "1"])
+def test_narrow_levels_pipelined_and_plain_agree_with_oracle(ctx, monkeypatch, pipe):
+    """The serial sponge (narrow levels) runs software-pipelined by default: at upload the terms of each row that read a wire solved one
+    level earlier are moved to the end of their lists, and the rest of a level is summed while the previous level finishes
+    (k_solve_narrow_pipe).  Both forms must give the oracle's wires -- on a chain long enough to have full rounds (13 instructions per
+    level, not pipelined), partial rounds (one instruction) and the chain's hand-over between permutations."""
+    monkeypatch.setenv("ZKPOR_NARROW_PIPE", pipe)
+    inst = circuit_instance(seed=41, **dict(MEDIUM, users=20, chain_perms=9))
+    prog = zk.Program(ctx, inst["flat"])
+    assert prog.stats()["narrow_levels"] > 1000
+    pk = make_pk(zk, ctx, inst)
+    ow, oa, ob, oc, _ = oracle_solution(inst)
+    for _ in range(2):
+        w, a, b, c, _ = prog.solve(inst["inputs_mont"], pk)
+        assert np.array_equal(w, ow) and np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(c, oc)
+    r, s = 5, 6
+    want, _ = orc.groth16_prove_program(inst["arr"], inst["flat"], inst["sc"]["infinity_a"], inst["sc"]["infinity_b"], inst["inputs_mont"], r, s)
+    assert pk.prove_solve(prog, inst["inputs_mont"], r, s) == want
+    prog.close(); pk.close()

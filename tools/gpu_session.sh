@@ -16,7 +16,7 @@ for st in $steps; do
     bench26cpu) timeout 1500 python bench.py > gpurun_out/s_bench26.json 2> gpurun_out/s_bench26.err; echo "bench26 rc=$?"; tail -c 2500 gpurun_out/s_bench26.json; tail -5 gpurun_out/s_bench26.err ;;
     ref26)   timeout 1700 python bench.py --impl reference > gpurun_out/s_ref26.json 2> gpurun_out/s_ref26.err; echo "ref26 rc=$?"; tail -c 1500 gpurun_out/s_ref26.json; tail -5 gpurun_out/s_ref26.err ;;
     ref24)   timeout 900 python bench.py --impl reference --log-n 24 > gpurun_out/s_ref24.json 2> gpurun_out/s_ref24.err; echo "ref24 rc=$?"; tail -c 1500 gpurun_out/s_ref24.json; tail -5 gpurun_out/s_ref24.err ;;
-    ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 30000 --csv --log-file gpurun_out/launches_bench22.csv python bench.py --log-n 22 --steps 1 --warmup 3 --no-cpu --no-e2e --no-parity > gpurun_out/s_ncu_l.log 2>&1; echo "ncu launches rc=$?" ;;
+    ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -k 'regex:^(?!k_solve_wide|k_solve_div).*' -c 4000 --csv --log-file gpurun_out/launches_bench22.csv python bench.py --log-n 22 --steps 1 --warmup 1 --provers 1 --no-cpu --no-e2e --no-parity > gpurun_out/s_ncu_l.log 2>&1; echo "ncu launches rc=$?" ;;
     solverbench22) timeout 600 python tools/solver_bench.py 22 > gpurun_out/s_solverbench22.log 2>&1; echo "solverbench22 rc=$?"; tail -8 gpurun_out/s_solverbench22.log | cut -c1-600 ;;
     solverbench26) timeout 900 python tools/solver_bench.py 26 96:512:9 96:512:0 > gpurun_out/s_solverbench26.log 2>&1; echo "solverbench26 rc=$?"; tail -4 gpurun_out/s_solverbench26.log | cut -c1-600 ;;
     sharded) timeout 600 python -m pytest tests/test_gpu_sharded.py -x -q > gpurun_out/s_sharded.log 2>&1; rc=$?; echo "sharded tests rc=$rc"; tail -25 gpurun_out/s_sharded.log
@@ -29,7 +29,7 @@ for st in $steps; do
     witness) timeout 900 python bench.py --workload witness > gpurun_out/s_witness.json 2> gpurun_out/s_witness.err; echo "witness rc=$?"; tail -c 2500 gpurun_out/s_witness.json; tail -5 gpurun_out/s_witness.err ;;
     witness_small) timeout 600 python bench.py --workload witness --accounts 400000 > gpurun_out/s_witness_small.json 2> gpurun_out/s_witness_small.err; echo "witness_small rc=$?"; tail -c 2500 gpurun_out/s_witness_small.json; tail -5 gpurun_out/s_witness_small.err ;;
     ncu_poseidon) timeout 900 ncu --set full --import-source on --clock-control none -k regex:'k_account_leaves_tpa|k_merkle_level|k_cex_commitments' --launch-skip 2 -c 6 -f -o gpurun_out/r02_poseidon python bench.py --workload witness --accounts 600000 > gpurun_out/s_ncu_poseidon.log 2>&1; echo "ncu poseidon rc=$?"; tail -3 gpurun_out/s_ncu_poseidon.log | cut -c1-300 ;;
-    ncu_accumulate) timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_accumulate --launch-skip 2 -c 2 -f -o gpurun_out/r02_accumulate python tools/ncu_traffic.py run 24 > gpurun_out/s_ncu_acc.log 2>&1; echo "ncu accumulate rc=$?"; tail -3 gpurun_out/s_ncu_acc.log | cut -c1-300 ;;
+    ncu_accumulate) timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_accumulate -c 4 -f -o gpurun_out/r02_accumulate python tools/ncu_traffic.py run 24 > gpurun_out/s_ncu_acc.log 2>&1; echo "ncu accumulate rc=$?"; tail -3 gpurun_out/s_ncu_acc.log | cut -c1-300 ;;
     ncu_narrow) timeout 900 ncu --set full --import-source on --clock-control none -k k_solve_narrow --launch-skip 6 -c 3 -f -o gpurun_out/r02_narrow python tools/solver_bench.py 22 96:512:9 > gpurun_out/s_ncu_narrow.log 2>&1; echo "ncu narrow rc=$?"; tail -3 gpurun_out/s_ncu_narrow.log | cut -c1-300 ;;
     *) echo "unknown step $st" ;;
   esac

@@ -30,6 +30,14 @@ static const uint32_t NARROW_MAX = 96;          // levels up to this many instru
 static const int NARROW_THREADS = 512;          // upper bound of the fused-run CTA (env ZKPOR_NARROW_THREADS picks fewer warps)
 static const uint64_t SOLVE_NONE = ~0ull;
 static const uint32_t HINT_BIT = 0x80000000u;
+// solve_e[row]: which term of the constraint is the unknown -- side in bits 62..63, position in the side's term list in bits 0..35 --
+// and, for rows of narrow levels, how many of each side's terms read a wire solved in the level just before (bits 36..59, eight per
+// side; those terms are moved to the end of the side's list at upload): everything else of a row can be summed one level ahead
+// (k_solve_narrow_pipe).  SE_ALLFRESH: a side has more than 255 such terms, nothing of the row is summed ahead.
+static const uint64_t SE_POS_MASK = (1ull << 36) - 1, SE_ALLFRESH = 1ull << 60;
+__host__ __device__ __forceinline__ int se_side(uint64_t se) { return (int)(se >> 62); }
+__host__ __device__ __forceinline__ uint64_t se_pos(uint64_t se) { return se & SE_POS_MASK; }
+__host__ __device__ __forceinline__ uint32_t se_fresh(uint64_t se, int side) { return (uint32_t)(se >> (36 + 8 * side)) & 255u; }
 
 enum StepKind { STEP_WIDE = 0, STEP_NARROW, STEP_COUNT, STEP_COMMIT };
 struct Step { int kind; uint64_t a, b; bool has_div; uint64_t n_long; };   // WIDE: sched range [a, b), the first n_long rows long; NARROW: levels [a, b); COUNT / COMMIT: hint id a
@@ -80,6 +88,7 @@ struct zkpor_program {
     uint32_t *tail_wires = nullptr, *tail_mask = nullptr; uint32_t *wstep = nullptr;
     std::vector<uint32_t> h_tail_wires;
     cudaEvent_t tail_go = nullptr, tail_done = nullptr; bool tail_running = false;
+    bool narrow_pipe = false;                      // narrow levels by k_solve_narrow_pipe (rows partitioned at upload)
     const char *trace_path = nullptr;              // env ZKPOR_SOLVE_TRACE: per-step device times of the next solve, written as CSV
 };
 
@@ -354,7 +363,7 @@ __device__ __forceinline__ void exec_instr(const ProgView &v, uint32_t packed, i
         if (total > 1) { if (lane == 0) solve_fail(v, SE_UNSOLVED, row); return; }
         if (total == 0) { if (lane == 0) v.solve_e[row] = SOLVE_NONE; return; }
         if (found) {
-            const int side = (int)(cand >> 62); const uint64_t pos = cand & ((1ull << 62) - 1);
+            const int side = se_side(cand); const uint64_t pos = se_pos(cand);
             v.solve_e[row] = cand; v.solved[v.wire[side][pos]] = 1; v.wstep[v.wire[side][pos]] = v.cur_step + 1;
             const uint32_t cid = v.coef[side][pos];
             if (step != NO_SLOT && (side != 2 || (cid != v.one_id && cid != v.minus_one_id))) v.step_div[step] = 1;
@@ -363,8 +372,8 @@ __device__ __forceinline__ void exec_instr(const ProgView &v, uint32_t packed, i
     }
     const uint64_t se = v.solve_e[row];
     if (se == SOLVE_NONE) return;                         // an assertion: checked with a, b, c after the solve
-    const int side = (int)(se >> 62);
-    const uint64_t pos = se & ((1ull << 62) - 1);
+    const int side = se_side(se);
+    const uint64_t pos = se_pos(se);
     const Fr a = group_dot<G>(v, v.ptr[0], v.wire[0], v.coef[0], row, side == 0 ? pos : SOLVE_NONE, lane, mask);
     const Fr b = group_dot<G>(v, v.ptr[1], v.wire[1], v.coef[1], row, side == 1 ? pos : SOLVE_NONE, lane, mask);
     const Fr c = group_dot<G>(v, v.ptr[2], v.wire[2], v.coef[2], row, side == 2 ? pos : SOLVE_NONE, lane, mask);
@@ -515,7 +524,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow(ProgView v, uin
             else {
                 se = v.solve_e[packed];
                 if (se != SOLVE_NONE) {
-                    const uint64_t skip = (int)(se >> 62) == side ? (se & ((1ull << 62) - 1)) : SOLVE_NONE;
+                    const uint64_t skip = se_side(se) == side ? se_pos(se) : SOLVE_NONE;
                     const Wide9 acc = group_sum_w9<32>(lane_dot_w9(v, v.ptr[side], v.wire[side], v.coef[side], packed, skip, prt * 32 + lane, sub * 32), 0xFFFFFFFFu);
                     if (lane == 0) for (int i = 0; i < 9; i++) part[ins][side][prt][i] = acc.l[i];
                 }
@@ -533,12 +542,162 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow(ProgView v, uin
             Fr b, c;
 #pragma unroll
             for (int i = 0; i < 8; i++) { b.l[i] = __shfl_sync(0xFFFFFFFFu, mine.l[i], 1); c.l[i] = __shfl_sync(0xFFFFFFFFu, mine.l[i], 2); }
-            if (lane == 0) finish_instr(v, packed, (int)(se >> 62), se & ((1ull << 62) - 1), mine, b, c, NO_SLOT);
+            if (lane == 0) finish_instr(v, packed, se_side(se), se_pos(se), mine, b, c, NO_SLOT);
         } else if (working == nwarps && !(warp < working && first)) {
             // no spare warp in this level: the warps that are not finishing prefetch while the finishers work
             narrow_prefetch(v, l, l1, warp, nwarps, lane);
         }
         __syncthreads();
+    }
+}
+
+// ---- narrow levels, software-pipelined --------------------------------------------------------------------------------------------
+// In the serial sponge a level is one S-box constraint whose sides are ~80-term linear expressions, but only the terms that read the
+// wire solved ONE level earlier (one or two) have to wait for it.  zkpor_program_upload moves those "fresh" terms to the end of each
+// side's list (solve_e carries their count); here the other ("old") terms of level l + 1 are summed by eleven warps WHILE the finishing
+// warp of level l reduces, multiplies and stores -- so a level's critical path is: the fresh terms' products, a small sum, the finish.
+// Levels of one to three instructions run this way; wider ones go warp-per-instruction as in k_solve_narrow.
+static const int PIPE_MAX_K = 3, PIPE_FIN0 = 11;     // finisher of instruction i = warp PIPE_FIN0 + i; warps 0..10 sum ahead
+
+// sum of the old terms of level l (k instructions) into oldp[ins][side][part]; warps 0 .. PIPE_FIN0-1
+__device__ __forceinline__ void pipe_old_phase(const ProgView &v, uint64_t s0, int k, int warp, int lane, uint32_t (*oldp)[3][3][12]) {
+    const int sub = k == 1 ? 3 : 1;
+    if (warp >= 3 * k * sub) return;
+    const int ins = k == 1 ? 0 : warp / 3, side = k == 1 ? warp / 3 : warp % 3, prt = k == 1 ? warp % 3 : 0;
+    const uint32_t packed = v.sched[s0 + ins];
+    Wide9 acc = w9_zero();
+    if (!(packed & HINT_BIT)) {
+        const uint64_t se = v.solve_e[packed];
+        if (se != SOLVE_NONE && !(se & SE_ALLFRESH)) {
+            const uint64_t e0 = v.ptr[side][packed], e1 = v.ptr[side][(uint64_t)packed + 1] - se_fresh(se, side);
+            const uint64_t skip = se_side(se) == side ? se_pos(se) : SOLVE_NONE;
+            for (uint64_t e = e0 + prt * 32 + lane; e < e1; e += sub * 32) {
+                if (e == skip) continue;
+                term_w9(v, acc, v.coef[side][e], v.w[v.wire[side][e]]);
+            }
+            acc = group_sum_w9<32>(acc, 0xFFFFFFFFu);
+        }
+    }
+    if (lane == 0) for (int i = 0; i < 9; i++) oldp[ins][side][prt][i] = acc.l[i];
+}
+
+__global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow_pipe(ProgView v, uint64_t l0, uint64_t l1) {
+    __shared__ uint32_t oldp[2][PIPE_MAX_K][3][3][12];
+    __shared__ uint32_t freshp[PIPE_MAX_K][3][12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;      // launched with 16 warps
+    bool have_old = false;
+    int cur = 0;
+    uint64_t s0 = v.lvl_start[l0];
+    for (uint64_t l = l0; l < l1; l++) {
+        const uint64_t s1 = v.lvl_start[l + 1];
+        const int k = (int)(s1 - s0);
+        if (k > PIPE_MAX_K) {
+            narrow_prefetch(v, l, l1, warp, nwarps, lane);
+            for (uint64_t p = s0 + warp; p < s1; p += nwarps) exec_instr<32, false>(v, v.sched[p], lane, 0xFFFFFFFFu, NO_SLOT, NO_SLOT);
+            __syncthreads();
+            have_old = false; s0 = s1;
+            continue;
+        }
+        if (!have_old) {                                    // first level of a pipelined stretch: its old terms were not summed ahead
+            if (warp < PIPE_FIN0) pipe_old_phase(v, s0, k, warp, lane, oldp[cur]);
+            __syncthreads();
+        }
+        // fresh terms: one warp per (instruction, side); the other warps prefetch the static data of the levels ahead
+        uint32_t packed = HINT_BIT;
+        uint64_t se = SOLVE_NONE;
+        if (warp < 3 * k) {
+            const int ins = warp / 3, side = warp % 3;
+            packed = v.sched[s0 + ins];
+            if (!(packed & HINT_BIT)) {
+                se = v.solve_e[packed];
+                if (se != SOLVE_NONE) {
+                    const uint64_t e1 = v.ptr[side][(uint64_t)packed + 1];
+                    const uint64_t e0 = (se & SE_ALLFRESH) ? v.ptr[side][packed] : e1 - se_fresh(se, side);
+                    const uint64_t skip = se_side(se) == side ? se_pos(se) : SOLVE_NONE;
+                    Wide9 acc = w9_zero();
+                    for (uint64_t e = e0 + lane; e < e1; e += 32) {
+                        if (e == skip) continue;
+                        term_w9(v, acc, v.coef[side][e], v.w[v.wire[side][e]]);
+                    }
+                    if (e1 - e0 > 1) acc = group_sum_w9<32>(acc, 0xFFFFFFFFu);
+                    if (lane == 0) for (int i = 0; i < 9; i++) freshp[ins][side][i] = acc.l[i];
+                }
+            }
+        } else narrow_prefetch(v, l, l1, warp - 3 * k, nwarps - 3 * k, lane);
+        __syncthreads();
+        // finish level l (warps PIPE_FIN0 ..) while warps 0 .. PIPE_FIN0-1 sum the old terms of level l + 1
+        const uint64_t s2 = l + 1 < l1 ? v.lvl_start[l + 2] : s1;
+        const int k1 = (int)(s2 - s1);
+        const bool pipe1 = l + 1 < l1 && k1 <= PIPE_MAX_K && k1 > 0;
+        if (warp >= PIPE_FIN0 && warp - PIPE_FIN0 < k) {
+            const int ins = warp - PIPE_FIN0;
+            const uint32_t pk = v.sched[s0 + ins];
+            if (pk & HINT_BIT) { if (lane == 0) exec_hint<false>(v, pk & ~HINT_BIT, NO_SLOT, NO_SLOT); }
+            else {
+                const uint64_t sq = v.solve_e[pk];
+                if (sq != SOLVE_NONE) {
+                    Fr mine = Fr::zero();
+                    if (lane < 3) {
+                        Wide9 t;
+                        for (int i = 0; i < 9; i++) t.l[i] = freshp[ins][lane][i];
+                        const int sub = k == 1 ? 3 : 1;
+                        for (int q = 0; q < sub; q++) { Wide9 o; for (int i = 0; i < 9; i++) o.l[i] = oldp[cur][ins][lane][q][i]; w9_addw(t, o); }
+                        mine = w9_reduce(t);
+                    }
+                    Fr b, c;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { b.l[i] = __shfl_sync(0xFFFFFFFFu, mine.l[i], 1); c.l[i] = __shfl_sync(0xFFFFFFFFu, mine.l[i], 2); }
+                    if (lane == 0) finish_instr(v, pk, se_side(sq), se_pos(sq), mine, b, c, NO_SLOT);
+                }
+            }
+        } else if (warp < PIPE_FIN0 && pipe1) pipe_old_phase(v, s1, k1, warp, lane, oldp[cur ^ 1]);
+        __syncthreads();
+        have_old = pipe1; cur ^= 1; s0 = s1;
+    }
+}
+
+// upload: wlevel[wire] = 1 + the level that solves it, for the wires solved in narrow levels [la, lb); one thread per level
+__global__ void k_narrow_wlevel(ProgView v, uint64_t la, uint64_t lb, uint32_t *wlevel) {
+    const uint64_t l = la + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= lb) return;
+    for (uint64_t p = v.lvl_start[l], p1 = v.lvl_start[l + 1]; p < p1; p++) {
+        const uint32_t packed = v.sched[p];
+        if (packed & HINT_BIT) {
+            const uint32_t h = packed & ~HINT_BIT;
+            for (uint32_t q = 0; q < v.hint_nout[h]; q++) wlevel[v.hint_out[h] + q] = (uint32_t)(l + 1);
+        } else {
+            const uint64_t se = v.solve_e[packed];
+            if (se != SOLVE_NONE) wlevel[v.wire[se_side(se)][se_pos(se)]] = (uint32_t)(l + 1);
+        }
+    }
+}
+// upload: in every row of the narrow levels [la, lb) the terms that read a wire solved one level earlier go to the end of their side's
+// list (a sum does not depend on the order of its terms); their count and the unknown's new position are recorded in solve_e
+__global__ void k_narrow_partition(ProgView v, uint64_t la, uint64_t lb, const uint32_t *__restrict__ wlevel) {
+    const uint64_t l = la + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= lb) return;
+    for (uint64_t p = v.lvl_start[l], p1 = v.lvl_start[l + 1]; p < p1; p++) {
+        const uint32_t packed = v.sched[p];
+        if (packed & HINT_BIT) continue;
+        uint64_t se = v.solve_e[packed];
+        if (se == SOLVE_NONE) continue;
+        const int us = se_side(se);
+        uint64_t upos = se_pos(se), out = (uint64_t)us << 62;
+        for (int side = 0; side < 3; side++) {
+            uint32_t *wi = const_cast<uint32_t *>(v.wire[side]), *ci = const_cast<uint32_t *>(v.coef[side]);
+            uint64_t i = v.ptr[side][packed], j = v.ptr[side][(uint64_t)packed + 1];
+            uint64_t nf = 0;
+            while (i < j) {
+                const bool fresh = !(side == us && i == upos) && wlevel[wi[i]] == (uint32_t)l;
+                if (!fresh) { i++; continue; }
+                j--;
+                const uint32_t tw = wi[i], tc = ci[i]; wi[i] = wi[j]; ci[i] = ci[j]; wi[j] = tw; ci[j] = tc;
+                if (side == us) { if (upos == j) upos = i; }        // the unknown's term sat at j and moved to i (i itself is fresh, never the unknown)
+                nf++;
+            }
+            if (nf > 255) out |= SE_ALLFRESH; else out |= nf << (36 + 8 * side);
+        }
+        v.solve_e[packed] = out | upos;
     }
 }
 
@@ -581,7 +740,7 @@ __global__ void k_tail_scan(ProgView v, uint64_t p0, uint64_t p1, uint32_t tail_
         const uint64_t se = v.solve_e[packed];
         if (se != SOLVE_NONE) {
             const unsigned long long at = atomicAdd(cursor, 1ull);
-            if (out_wires) out_wires[at] = v.wire[(int)(se >> 62)][se & ((1ull << 62) - 1)];
+            if (out_wires) out_wires[at] = v.wire[se_side(se)][se_pos(se)];
         }
     }
     if (d) atomicMax(dep, d);
@@ -658,7 +817,8 @@ static int32_t run_schedule(zkpor_ctx *ctx, zkpor_program *p, zkpor_pk *pk, Fr *
             ctx->stream = ctx->tail_stream;
             int32_t rc = ZKPOR_OK;
             { KTimed kt(ctx, KC_SOLVE_NARROW, t.b - t.a);
-              k_solve_narrow<false><<<1, p->narrow_threads, 0, ctx->stream>>>(v, t.a, t.b);
+              if (p->narrow_pipe) k_solve_narrow_pipe<<<1, NARROW_THREADS, 0, ctx->stream>>>(v, t.a, t.b);
+              else k_solve_narrow<false><<<1, p->narrow_threads, 0, ctx->stream>>>(v, t.a, t.b);
               ctx->launches++;
               if (cudaGetLastError() != cudaSuccess) { set_error("solve: launch of the deferred tail failed"); rc = ZKPOR_ERR_CUDA; }
               kt.stop(); }
@@ -679,7 +839,8 @@ static int32_t run_schedule(zkpor_ctx *ctx, zkpor_program *p, zkpor_pk *pk, Fr *
         }
         case STEP_NARROW: {
             KTimed kt(ctx, KC_SOLVE_NARROW, DRY ? 0 : s.b - s.a);
-            ZK_LAUNCH(ctx, k_solve_narrow<DRY>, 1, p->narrow_threads, 0, v, s.a, s.b);
+            if (!DRY && p->narrow_pipe) ZK_LAUNCH(ctx, k_solve_narrow_pipe, 1, NARROW_THREADS, 0, v, s.a, s.b);
+            else ZK_LAUNCH(ctx, k_solve_narrow<DRY>, 1, p->narrow_threads, 0, v, s.a, s.b);
             kt.stop();
             break;
         }
@@ -962,6 +1123,22 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
     }
     cudaFree(solved);
     if (rc != ZKPOR_OK) return fail(rc);
+    // narrow levels: move each row's fresh terms (wires solved one level earlier) to the end of their lists (k_solve_narrow_pipe)
+    {
+        const char *e = getenv("ZKPOR_NARROW_PIPE");
+        p->narrow_pipe = (e == nullptr || atoi(e) != 0) && p->narrow_threads == NARROW_THREADS && p->stats[2] > 0;
+    }
+    if (p->narrow_pipe) {
+        uint32_t *wlevel = nullptr;
+        if (cudaMalloc((void **)&wlevel, d->n_wires * 4) != cudaSuccess) { set_error("program_upload: out of device memory"); return fail(ZKPOR_ERR_OOM); }
+        cudaMemsetAsync(wlevel, 0, d->n_wires * 4, ctx->stream);
+        ProgView v = make_view(p, nullptr, nullptr);
+        for (const Step &st : p->steps) if (st.kind == STEP_NARROW) k_narrow_wlevel<<<grid_for(st.b - st.a, 128), 128, 0, ctx->stream>>>(v, st.a, st.b, wlevel);
+        for (const Step &st : p->steps) if (st.kind == STEP_NARROW) k_narrow_partition<<<grid_for(st.b - st.a, 128), 128, 0, ctx->stream>>>(v, st.a, st.b, wlevel);
+        const cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+        cudaFree(wlevel);
+        if (ce != cudaSuccess) { set_error("program_upload: narrow-level analysis failed: %s", cudaGetErrorString(ce)); return fail(ZKPOR_ERR_CUDA); }
+    }
     // the deferred tail: the last step, if it is a long run of narrow levels
     uint64_t tail_min = 2048;
     if (const char *e = getenv("ZKPOR_TAIL_MIN")) tail_min = (uint64_t)std::max(0, atoi(e));   // 0: never defer
