@@ -156,7 +156,7 @@ def test_deferred_tail_gives_the_same_proof(ctx, monkeypatch):
 
 @pytest.mark.parametrize("pipe", ["0", "1"])
 def test_narrow_levels_pipelined_and_plain_agree_with_oracle(ctx, monkeypatch, pipe):
-    """The serial sponge (narrow levels) runs software-pipelined by default: at upload the terms of each row that read a wire solved one
+    """The serial sponge (narrow levels) can run software-pipelined (ZKPOR_NARROW_PIPE=1; opt-in): at upload the terms of each row that read a wire solved one
     level earlier are moved to the end of their lists, and the rest of a level is summed while the previous level finishes
     (k_solve_narrow_pipe).  Both forms must give the oracle's wires -- on a chain long enough to have full rounds (13 instructions per
     level, not pipelined), partial rounds (one instruction) and the chain's hand-over between permutations."""

@@ -55,6 +55,7 @@ struct ProgView {
     Fr *w; uint8_t *solved; unsigned long long *err;      // err: (code << 56) | row or hint id, first writer wins
     struct Pending *pend;                                 // wide levels: divisions deferred to k_solve_div, slot = position in the level
     uint8_t *step_div;                                    // dry run: step s has at least one division
+    unsigned long long *prof;                             // ZKPOR_NARROW_PROF: cycle counters of k_solve_narrow_pipe's phases (development)
     uint32_t *wstep; uint32_t cur_step;                   // dry run: wstep[wire] = 1 + the schedule step that solves it (0: an input)
 };
 // w[wire] = num / den, written by the evaluating group, consumed (and cleared) by k_solve_div
@@ -88,6 +89,7 @@ struct zkpor_program {
     uint32_t *tail_wires = nullptr, *tail_mask = nullptr; uint32_t *wstep = nullptr;
     std::vector<uint32_t> h_tail_wires;
     cudaEvent_t tail_go = nullptr, tail_done = nullptr; bool tail_running = false;
+    unsigned long long *prof = nullptr;
     bool narrow_pipe = false;                      // narrow levels by k_solve_narrow_pipe (rows partitioned at upload)
     const char *trace_path = nullptr;              // env ZKPOR_SOLVE_TRACE: per-step device times of the next solve, written as CSV
 };
@@ -374,6 +376,26 @@ __device__ __forceinline__ void exec_instr(const ProgView &v, uint32_t packed, i
     if (se == SOLVE_NONE) return;                         // an assertion: checked with a, b, c after the solve
     const int side = se_side(se);
     const uint64_t pos = se_pos(se);
+    if (G == 32) {
+        // both products' sides fit a half-warp (the full rounds of a Poseidon permutation: 13 terms): L on lanes 0..15 and R on lanes
+        // 16..31 at once, one term per lane -- a third of the serial work of three whole-warp sums
+        const uint64_t a0 = v.ptr[0][row], a1 = v.ptr[0][row + 1], b0 = v.ptr[1][row], b1 = v.ptr[1][row + 1];
+        if (a1 - a0 <= 16 && b1 - b0 <= 16) {
+            const int half = lane >> 4, hl = lane & 15;
+            const uint64_t e = (half ? b0 : a0) + hl, e1 = half ? b1 : a1;
+            Wide9 acc = w9_zero();
+            if (e < e1 && !(side == half && e == pos)) term_w9(v, acc, (half ? v.coef[1] : v.coef[0])[e], v.w[(half ? v.wire[1] : v.wire[0])[e]]);
+            acc = group_sum_w9<16>(acc, mask);
+            const Fr mine = hl == 0 ? w9_reduce(acc) : Fr::zero();
+            Fr bb;
+#pragma unroll
+            for (int i = 0; i < 8; i++) bb.l[i] = __shfl_sync(mask, mine.l[i], 16);
+            const uint64_t c0 = v.ptr[2][row], c1 = v.ptr[2][row + 1];
+            const Fr cc = (side == 2 && c1 - c0 == 1) ? Fr::zero() : group_dot<G>(v, v.ptr[2], v.wire[2], v.coef[2], row, side == 2 ? pos : SOLVE_NONE, lane, mask);
+            if (lane == 0) finish_instr(v, row, side, pos, mine, bb, cc, slot);
+            return;
+        }
+    }
     const Fr a = group_dot<G>(v, v.ptr[0], v.wire[0], v.coef[0], row, side == 0 ? pos : SOLVE_NONE, lane, mask);
     const Fr b = group_dot<G>(v, v.ptr[1], v.wire[1], v.coef[1], row, side == 1 ? pos : SOLVE_NONE, lane, mask);
     const Fr c = group_dot<G>(v, v.ptr[2], v.wire[2], v.coef[2], row, side == 2 ? pos : SOLVE_NONE, lane, mask);
@@ -588,13 +610,17 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow_pipe(ProgView v
     bool have_old = false;
     int cur = 0;
     uint64_t s0 = v.lvl_start[l0];
+    long long pf[6] = {0, 0, 0, 0, 0, 0}, tq = 0;          // prof: [0] fresh work, [1] wait at barrier 1, [2] finish / old work, [3] wait at barrier 2, [4] pipelined levels, [5] other levels' cycles
+    const bool prof = v.prof != nullptr && lane == 0 && (warp == 0 || warp == PIPE_FIN0);
     for (uint64_t l = l0; l < l1; l++) {
         const uint64_t s1 = v.lvl_start[l + 1];
         const int k = (int)(s1 - s0);
+        if (prof) tq = clock64();
         if (k > PIPE_MAX_K) {
             narrow_prefetch(v, l, l1, warp, nwarps, lane);
             for (uint64_t p = s0 + warp; p < s1; p += nwarps) exec_instr<32, false>(v, v.sched[p], lane, 0xFFFFFFFFu, NO_SLOT, NO_SLOT);
             __syncthreads();
+            if (prof) pf[5] += clock64() - tq;
             have_old = false; s0 = s1;
             continue;
         }
@@ -624,7 +650,9 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow_pipe(ProgView v
                 }
             }
         } else narrow_prefetch(v, l, l1, warp - 3 * k, nwarps - 3 * k, lane);
+        if (prof) { const long long t = clock64(); pf[0] += t - tq; tq = t; }
         __syncthreads();
+        if (prof) { const long long t = clock64(); pf[1] += t - tq; tq = t; }
         // finish level l (warps PIPE_FIN0 ..) while warps 0 .. PIPE_FIN0-1 sum the old terms of level l + 1
         const uint64_t s2 = l + 1 < l1 ? v.lvl_start[l + 2] : s1;
         const int k1 = (int)(s2 - s1);
@@ -651,9 +679,12 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_solve_narrow_pipe(ProgView v
                 }
             }
         } else if (warp < PIPE_FIN0 && pipe1) pipe_old_phase(v, s1, k1, warp, lane, oldp[cur ^ 1]);
+        if (prof) { const long long t = clock64(); pf[2] += t - tq; tq = t; }
         __syncthreads();
+        if (prof) { pf[3] += clock64() - tq; pf[4]++; }
         have_old = pipe1; cur ^= 1; s0 = s1;
     }
+    if (prof) for (int i = 0; i < 6; i++) atomicAdd(v.prof + (warp == 0 ? 0 : 6) + i, (unsigned long long)pf[i]);
 }
 
 // upload: wlevel[wire] = 1 + the level that solves it, for the wires solved in narrow levels [la, lb); one thread per level
@@ -776,7 +807,7 @@ static ProgView make_view(zkpor_program *p, Fr *w, uint8_t *solved) {
     v.sched = p->sched; v.lvl_start = p->lvl_start;
     v.hint_fn = p->hint_fn; v.hint_param = p->hint_param; v.hint_out = p->hint_out; v.hint_nout = p->hint_nout; v.hint_in0 = p->hint_in0; v.hint_in1 = p->hint_in1;
     v.table_ptr = p->table_ptr; v.solve_e = p->solve_e; v.w = w; v.solved = solved; v.err = p->err;
-    v.pend = p->pend; v.step_div = p->step_div; v.wstep = p->wstep; v.cur_step = 0;
+    v.pend = p->pend; v.step_div = p->step_div; v.wstep = p->wstep; v.cur_step = 0; v.prof = p->prof;
     return v;
 }
 
@@ -935,6 +966,17 @@ int32_t zkpor_program_free(zkpor_ctx *ctx, zkpor_program *p) {
                     p->hint_in0, p->hint_in1, p->table_ptr, p->solve_e, p->err, p->counters, p->pend, p->step_div};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (p->tail_running) cudaStreamSynchronize(ctx->tail_stream);
+    if (p->prof) {
+        unsigned long long h[12];
+        cudaDeviceSynchronize();
+        if (cudaMemcpy(h, p->prof, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (int wv = 0; wv < 2; wv++) {
+                const double n = (double)std::max<unsigned long long>(h[6 * wv + 4], 1);
+                fprintf(stderr, "narrow prof, %s: per pipelined level: work A %.0f | wait 1 %.0f | work B %.0f | wait 2 %.0f cycles (%llu levels); other levels %.0f cycles in all\n",
+                        wv == 0 ? "warp 0 (fresh terms, old terms)" : "finisher warp", h[6 * wv] / n, h[6 * wv + 1] / n, h[6 * wv + 2] / n, h[6 * wv + 3] / n, h[6 * wv + 4], (double)h[6 * wv + 5]);
+            }
+        cudaFree(p->prof);
+    }
     for (void *q : {(void *)p->tail_wires, (void *)p->tail_mask, (void *)p->wstep}) if (q) cudaFree(q);
     if (p->tail_go) cudaEventDestroy(p->tail_go);
     if (p->tail_done) cudaEventDestroy(p->tail_done);
@@ -1023,6 +1065,7 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
     if (const char *e = getenv("ZKPOR_NARROW_MAX")) p->narrow_max = (uint32_t)std::max(1, atoi(e));
     if (const char *e = getenv("ZKPOR_NARROW_THREADS")) p->narrow_threads = std::min(NARROW_THREADS, std::max(32, atoi(e) & ~31));
     p->trace_path = getenv("ZKPOR_SOLVE_TRACE");
+    if (getenv("ZKPOR_NARROW_PROF")) { if (cudaMalloc((void **)&p->prof, 12 * 8) == cudaSuccess) cudaMemset(p->prof, 0, 12 * 8); else p->prof = nullptr; }
     p->long_row = WIDE_LONG_ROW;
     if (const char *e = getenv("ZKPOR_WIDE_LONG_ROW")) p->long_row = (uint32_t)std::max(0, atoi(e));   // 0: every row takes a warp
     // schedule: instructions in level order, special hints lifted out as steps of their own
@@ -1126,7 +1169,7 @@ int32_t zkpor_program_upload(zkpor_ctx *ctx, const zkpor_program_desc *d, zkpor_
     // narrow levels: move each row's fresh terms (wires solved one level earlier) to the end of their lists (k_solve_narrow_pipe)
     {
         const char *e = getenv("ZKPOR_NARROW_PIPE");
-        p->narrow_pipe = (e == nullptr || atoi(e) != 0) && p->narrow_threads == NARROW_THREADS && p->stats[2] > 0;
+        p->narrow_pipe = e != nullptr && atoi(e) != 0 && p->narrow_threads == NARROW_THREADS && p->stats[2] > 0;   // opt-in: measured 4 % slower
     }
     if (p->narrow_pipe) {
         uint32_t *wlevel = nullptr;
