@@ -166,6 +166,48 @@ inline std::vector<uint8_t> ProveWires(Context &ctx, ProvingKey &pk, R1cs &cs, c
     out.resize(n);
     return out;
 }
+// gnark's compiled constraint system, flattened (zkpor_program_desc): the witness solver's program resident in HBM
+class Program {
+  public:
+    Program(Context &ctx, const zkpor_program_desc &desc) : ctx_(ctx) { check(zkpor_program_upload(ctx.get(), &desc, &h_)); }
+    ~Program() { zkpor_program_free(ctx_.get(), h_); }
+    Program(const Program &) = delete;
+    zkpor_program *get() const { return h_; }
+    // r1cs.Solve: inputs = public then secret values; any output may be null
+    void Solve(ProvingKey *pk, const void *inputs, void *wires, void *a, void *b, void *c, void *commitment64 = nullptr) {
+        check(zkpor_r1cs_solve(ctx_.get(), h_, pk ? pk->get() : nullptr, inputs, wires, a, b, c, commitment64));
+    }
+  private:
+    Context &ctx_; zkpor_program *h_ = nullptr;
+};
+// the whole of groth16.Prove (src/prover/prover/prover.go:269): witness solver with its hints, commitment mid-solve, proof
+inline std::vector<uint8_t> ProveSolve(Context &ctx, ProvingKey &pk, Program &prog, const void *inputs, const Hash &r, const Hash &s) {
+    std::vector<uint8_t> out(388); uint32_t n = 0;
+    check(zkpor_groth16_prove_solve(ctx.get(), pk.get(), prog.get(), inputs, r.data(), s.data(), out.data(), &n));
+    out.resize(n);
+    return out;
+}
+// proof.ReadFrom (src/verifier/main.go:208-216): compressed or raw bytes -> the raw layout Verify takes; WriteTo / WriteRawTo back
+inline std::vector<uint8_t> DecodeProof(Context &ctx, const std::vector<uint8_t> &bytes) {
+    std::vector<uint8_t> out(260 + 64 * 17); uint32_t n = (uint32_t)out.size();
+    check(zkpor_proof_decode(ctx.get(), bytes.data(), bytes.size(), out.data(), &n, nullptr));
+    out.resize(n);
+    return out;
+}
+inline std::vector<uint8_t> EncodeProof(Context &ctx, const std::vector<uint8_t> &proof, bool compressed) {
+    std::vector<uint8_t> out(260 + 64 * 17); uint32_t n = (uint32_t)out.size();
+    check(zkpor_proof_encode(ctx.get(), proof.data(), (uint32_t)proof.size(), compressed ? 1 : 0, out.data(), &n));
+    out.resize(n);
+    return out;
+}
+// pk.WriteTo / WriteRawTo from the resident key (src/keygen/main.go:46-62)
+inline std::vector<uint8_t> WriteProvingKey(Context &ctx, ProvingKey &pk, bool raw) {
+    uint64_t n = 0;
+    check(zkpor_pk_write(ctx.get(), pk.get(), raw ? 1 : 0, nullptr, 0, &n));
+    std::vector<uint8_t> out(n);
+    check(zkpor_pk_write(ctx.get(), pk.get(), raw ? 1 : 0, out.data(), out.size(), &n));
+    return out;
+}
 // groth16.Verify (src/prover/prover/prover.go:276, src/verifier/main.go:284): true = valid; a malformed proof throws.
 // public_witness: n_public Montgomery fr.Elements, without the ONE wire.
 inline bool Verify(Context &ctx, const zkpor_vk_desc &vk, const std::vector<uint8_t> &proof_raw, const void *public_witness, uint64_t n_public) {
@@ -188,6 +230,21 @@ inline bool VerifyBatch(Context &ctx, const zkpor_vk_desc &vk, const std::vector
     return ok != 0;
 }
 }  // namespace groth16
+
+namespace witness {
+// the witness service's main loop for all batches of one tier (src/witness/witness/witness.go:144-206)
+struct Batches { std::vector<uint64_t> totals; std::vector<Hash> cex_commitments, batch_commitments; };
+inline Batches RunBatches(Context &ctx, const zkpor_cex_desc &cex, const Hash &root, const std::vector<uint64_t> &flat_assets,
+                          const std::vector<uint32_t> &account_indices, uint32_t tier, uint32_t ops_per_batch) {
+    if (ops_per_batch == 0 || account_indices.size() % ops_per_batch != 0) throw Error("zkpor: the accounts must fill whole batches");
+    const size_t nb = account_indices.size() / ops_per_batch;
+    Batches out;
+    out.totals.resize((nb + 1) * (size_t)cex.n_assets * 5); out.cex_commitments.resize(nb + 1); out.batch_commitments.resize(nb);
+    check(zkpor_witness_batches(ctx.get(), &cex, root.data(), flat_assets.data(), account_indices.data(), account_indices.size(), tier, ops_per_batch,
+                                out.totals.data(), out.cex_commitments.data(), out.batch_commitments.data()));
+    return out;
+}
+}  // namespace witness
 
 // bn254.PairingCheck: prod e(P_i, Q_i) == 1
 inline bool PairingCheck(Context &ctx, const void *g1_points, const void *g2_points, uint64_t n) {
