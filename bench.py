@@ -3,12 +3,14 @@
 
 Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`, one JSON line on rank 0.
 
-One "step" = one pass of the hot path = the WHOLE of groth16.Prove (src/prover/prover/prover.go:269) for one batch, through the
-C-ABI call zkpor_groth16_prove_solve, from the circuit's inputs (the 1 public + ~4 M secret values gnark's witness holds):
-  witness solver on the device (level schedule, hints, the BSB22 commitment mid-solve) -> a = Lw, b = Rw, c = Ow ->
-  computeH (7 NTTs of size 2^26 + pointwise) -> the proof's multi-scalar multiplications (A, B1, K, Z in G1, B in G2; the
-  Pedersen commitment and its proof of knowledge come from the solve) -> 388 proof bytes.
+One "step" = one pass of the hot path = the WHOLE of groth16.Prove (src/prover/prover/prover.go:269) for one batch PER PROVER, through
+the C-ABI call zkpor_groth16_prove_solve, from the circuit's inputs (the 1 public + ~2 M secret values gnark's witness holds):
+  witness solver on the device (level schedule, hints, the BSB22 commitment mid-solve; its serial tail runs beside the
+  multiplications) -> a = Lw, b = Rw, c = Ow -> computeH (7 NTTs of size 2^26 + pointwise) -> the proof's multi-scalar
+  multiplications (A, B1, K, Z in G1, B in G2) -> 388 proof bytes.
 The proving key and the compiled constraint system are resident in HBM (as gnark keeps pk and r1cs in memory across proofs).
+--provers P (default 2): P provers per GPU, each with its own context, key and program, prove independent batches from P host
+threads (the reference runs several prover processes per machine, README.md:126); `one_proof_alone_ms` is one prover's latency.
 
 Workload.  gnark's frontend is Go and cannot compile circuit/batch_create_user_circuit.go here, so the constraint system is a
 BatchCreateUser-SHAPED synthetic one (circuit_synth.batch_create_user_like: per-user blocks of 50 assets with range checks, tier
@@ -17,23 +19,24 @@ serial sponge chain; one commitment with two log-derivative arguments), sized to
 (README.md:10-21).  The key is synthetic too: points (k0 + i*d)*G per array, so the timed proof can be checked EXACTLY by
 discrete-log arithmetic (`parity` in the JSON line; the run fails if it does not hold).
 
-  value  : proofs/hour, inputs already resident in HBM when the timed region starts.
+  value  : proofs/hour, inputs already resident in HBM when the timed region starts (device time between two full synchronisations).
   e2e    : same call with PINNED HOST inputs -- the H2D copy of the inputs and the D2H of the 388 proof bytes are inside the
-           timed region (the solver runs on the device, so only ~130 MB cross PCIe per proof).
+           timed region (the solver runs on the device, so only ~66 MB cross PCIe per proof).
   roofline: dominant kernel = G1 bucket accumulation (k_accumulate<Fp>); achieved = 96 B/term (64 B affine
            point + 32 B scalar) x terms per launch / CUDA-event duration per launch, against the measured HBM copy bandwidth
            in MEASURED_PEAKS.json.  The kernel is integer-ALU bound, so the fraction is ~1%: `modmul_roofline`
            carries achieved field multiplications per second against the measured IMAD.WIDE ceiling.
-  cpu_baseline: the oracle's CPU prover (oracle/c: the same solver walk over the host threads, Pippenger MSM, radix-2 NTT -- a
-           restatement of gnark's algorithm; gnark itself cannot be built here: no Go toolchain, modules not vendored) on a
-           bounded sample: the same circuit family on a 2^--cpu-log-n domain, time scaled by the constraint ratio.
+  cpu_baseline: the oracle's CPU prover (oracle/c: the same solver walk over the host threads, signed-digit Pippenger MSM,
+           radix-2 NTT -- a restatement of gnark's algorithm; gnark itself cannot be built here: no Go toolchain, modules not
+           vendored) on a bounded sample: the same circuit family on a 2^--cpu-log-n domain, time scaled by the constraint ratio.
   --impl reference: ONE full-size proof (same 2^26 circuit, same key) by that CPU prover on all host threads -- a measurement,
            not an extrapolation; steps/warmup are ignored beyond that (a 2^26 CPU proof takes minutes).
+  --workload witness: the witness service's hot path on --accounts synthetic accounts (tools/witness_bench.py).
 
 N > 1 (torchrun, one rank per GPU): proofs are independent objects (the reference scales the same way: several prover
-processes pulling batches from one queue, README.md:126) -- every rank holds a full key and proves its own batch each step;
-no data-path collective; value = N*K proofs / max-over-ranks time; scaling = "weak".  The same line carries `sharded`: ONE
-proof across the N GPUs through the library's own NCCL path.
+processes pulling batches from one queue, README.md:126) -- every rank holds full keys and proves its own batches each step;
+no data-path collective; value = N*P*K proofs / max-over-ranks time; scaling = "weak".  The same line carries `sharded`: ONE
+proof across the N GPUs through the library's own NCCL path, whole call and post-solver part.
 """
 import argparse
 import json
@@ -585,7 +588,7 @@ def main():
                        "key": "synthetic key in HBM: points (k0 + i*d)*G per array", "timing": "CUDA events on the library stream, max over ranks",
                        "setup_s": wl.setup_s},
             "solve_ms": solve_ms, "one_proof_alone_ms": solo_ms, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "modmul_roofline": modmul, "kernel_breakdown": breakdown,
-            "stage_ms": {k: float(np.mean([st.get(k, 0.0) for st in stages])) for k in (stages[0] if stages else {})},
+            "stage_ms": {k: float(np.mean([st.get(k, 0.0) for st in stages])) for k in ("h2d", "solve", "ntt") if stages and k in stages[0]},
             "wall_ms_per_step": wall / args.steps * 1e3, "proof_sha": __import__("hashlib").sha256(proof).hexdigest()[:16]}
     if e2e:
         line["e2e"] = e2e
