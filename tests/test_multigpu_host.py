@@ -74,3 +74,63 @@ def test_chunk_bounds_cover_exactly():
             cuts = [zk.chunk_bounds(L, r, world) for r in range(world)]
             assert cuts[0][0] == 0 and cuts[-1][1] == L
             assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+
+
+def _tree_worker(rank, world, port, capacity, depth, q):
+    """one tree over `world` ranks as zkpor_tree_build_sharded does it: own leaf range -> subtree root (the oracle hashes here: no GPU in
+    this container) -> all-gather of the subtree roots -> the top levels on every rank"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "py"))
+    import merkle
+    from bn254 import SplitMix64
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = SplitMix64(4242)
+        leaves = orc.be32_array([rng.field(R) for _ in range(capacity)])
+        nil = merkle.nil_account_hash()
+        first, count, k = zk.tree_shard_range(rank, world, capacity, depth)
+        # the subtree above my leaves is a depth-k tree of its own
+        if count:
+            _, sub_root = orc.merkle_build(leaves[first:first + count].copy(), count, k, nil)
+        else:                                        # a rank without leaves contributes the empty subtree of level k
+            sub_root = nil
+            for _ in range(k):
+                sub_root = orc.poseidon_node_batch(np.frombuffer(sub_root + sub_root, dtype=np.uint8).copy())[0].tobytes()
+        gathered = [torch.zeros(32, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(np.frombuffer(sub_root, dtype=np.uint8).copy()))
+        # top levels: a tree of depth - k over the `world` subtree roots, its empty leaves being the empty subtree of level k
+        nil_k = nil
+        for _ in range(k):
+            nil_k = orc.poseidon_node_batch(np.frombuffer(nil_k + nil_k, dtype=np.uint8).copy())[0].tobytes()
+        tops = torch.stack(gathered).numpy()
+        have = min(world, -(-capacity // (1 << k)))
+        _, root = orc.merkle_build(tops[:have].copy(), have, depth - k, nil_k)
+        _, want = orc.merkle_build(leaves, capacity, depth, nil)
+        q.put((rank, root == want, first, count))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("capacity", [1000, 3])
+def test_sharded_tree_split_gloo_world2(capacity):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + capacity) % 2000
+    procs = [ctx.Process(target=_tree_worker, args=(rk, 2, port, capacity, 28, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    assert [r[1] for r in res] == [True, True]
+    assert sum(r[3] for r in res) == capacity and res[0][2] == 0
+
+
+def test_tree_shard_ranges_cover_exactly():
+    for capacity in (1, 2, 3, 777, 1000, 10_000_000):
+        for world in (1, 2, 4, 8):
+            parts = [zk.tree_shard_range(r, world, capacity, 28) for r in range(world)]
+            assert sum(p[1] for p in parts) == capacity
+            assert all(p[0] == r << p[2] or p[1] == 0 for r, p in enumerate(parts))
+            assert len({p[2] for p in parts}) == 1 and (world << parts[0][2]) >= capacity

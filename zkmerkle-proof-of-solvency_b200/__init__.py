@@ -964,6 +964,18 @@ def multi_prove_solve(ctxs, pks, progs, inputs, r: int, s: int) -> bytes:
     return out[:ln.value].tobytes()
 
 
+def tree_shard_range(rank: int, world: int, capacity: int, depth: int):
+    """host mirror of zkpor_tree_shard_range: (first key, number of keys, subtree level k) of a rank when one tree is built over
+    `world` GPUs -- k is the smallest level with world << k >= capacity; rank g owns the leaves [g << k, (g + 1) << k)"""
+    k = 0
+    while k < depth and (world << k) < capacity:
+        k += 1
+    first = rank << k
+    if first >= capacity:
+        return capacity, 0, k
+    return first, min(1 << k, capacity - first), k
+
+
 def run_ranks(fn, n: int) -> list:
     """fn(rank) on n host threads (ctypes calls release the GIL, so collective library calls proceed concurrently); re-raises the
     first failure"""

@@ -10,18 +10,32 @@ using namespace ff;
 
 namespace zk {
 
+// <row, w>.  A thread's loads are a chain (row pointer -> term ids -> wire values) and a compiled circuit's rows have three terms on
+// average, so the gathers of four terms are issued together before any of them is used: the kernel is bound by the latency of
+// those gathers, not by their bytes.
+__device__ __forceinline__ Fr row_dot(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ wire_ids, const uint32_t *__restrict__ coeff_ids,
+                                      const Fr *__restrict__ coeffs, uint32_t one_id, const Fr *__restrict__ w, uint64_t row) {
+    Fr acc = Fr::zero();
+    const uint64_t end = row_ptr[row + 1];
+    for (uint64_t e = row_ptr[row]; e < end; e += 4) {
+        uint32_t id[4], wi[4];
+        Fr v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const bool on = e + k < end; id[k] = on ? __ldg(coeff_ids + e + k) : one_id; wi[k] = on ? __ldg(wire_ids + e + k) : 0xFFFFFFFFu; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = wi[k] != 0xFFFFFFFFu ? w[wi[k]] : Fr::zero();
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (wi[k] != 0xFFFFFFFFu) acc = Fr::add(acc, id[k] == one_id ? v[k] : Fr::mul(coeffs[id[k]], v[k]));
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(256) k_r1cs_rows(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ wire_ids,
                                                    const uint32_t *__restrict__ coeff_ids, const Fr *__restrict__ coeffs, uint32_t one_id,
                                                    const Fr *__restrict__ w, uint64_t n_rows, Fr *__restrict__ out) {
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_rows) return;
-    Fr acc = Fr::zero();
-    for (uint64_t e = row_ptr[row], end = row_ptr[row + 1]; e < end; e++) {
-        const uint32_t id = __ldg(coeff_ids + e);
-        const Fr v = w[__ldg(wire_ids + e)];
-        acc = Fr::add(acc, id == one_id ? v : Fr::mul(coeffs[id], v));
-    }
-    out[row] = acc;
+    out[row] = row_dot(row_ptr, wire_ids, coeff_ids, coeffs, one_id, w, row);
 }
 
 // j-th output = row offset + j*stride (the cyclic subsequence a rank of the distributed computeH holds); rows past the end are zero
@@ -32,14 +46,7 @@ __global__ void __launch_bounds__(256) k_r1cs_rows_strided(const uint64_t *__res
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
     const uint64_t row = offset + j * stride;
-    Fr acc = Fr::zero();
-    if (row < n_rows)
-        for (uint64_t e = row_ptr[row], end = row_ptr[row + 1]; e < end; e++) {
-            const uint32_t id = __ldg(coeff_ids + e);
-            const Fr v = w[__ldg(wire_ids + e)];
-            acc = Fr::add(acc, id == one_id ? v : Fr::mul(coeffs[id], v));
-        }
-    out[j] = acc;
+    out[j] = row < n_rows ? row_dot(row_ptr, wire_ids, coeff_ids, coeffs, one_id, w, row) : Fr::zero();
 }
 
 int32_t r1cs_eval_strided_dev(zkpor_ctx *ctx, zkpor_r1cs *cs, const Fr *d_wires, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t offset, uint64_t stride,
