@@ -10,32 +10,39 @@ using namespace ff;
 
 namespace zk {
 
-// <row, w>.  A thread's loads are a chain (row pointer -> term ids -> wire values) and a compiled circuit's rows have three terms on
-// average, so the gathers of four terms are issued together before any of them is used: the kernel is bound by the latency of
-// those gathers, not by their bytes.
+// <row, w> by ROW_LANES lanes: lane j takes the terms j, j + ROW_LANES, ... and the partial sums meet by shuffles.  A compiled
+// circuit mixes three-term rows with the ~80-term rows of its Poseidon gadgets: a thread per row would walk the long ones serially
+// while the other lanes of its warp idle; four lanes per row cut that walk by four and cost the short rows nothing but idle lanes.
+// The kernel is bound by the latency of the gathered 32-byte wire values, not by their bytes.
+static const int ROW_LANES = 4;
 __device__ __forceinline__ Fr row_dot(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ wire_ids, const uint32_t *__restrict__ coeff_ids,
-                                      const Fr *__restrict__ coeffs, uint32_t one_id, const Fr *__restrict__ w, uint64_t row) {
+                                      const Fr *__restrict__ coeffs, uint32_t one_id, const Fr *__restrict__ w, uint64_t row, bool live, int lane) {
     Fr acc = Fr::zero();
-    const uint64_t end = row_ptr[row + 1];
-    for (uint64_t e = row_ptr[row]; e < end; e += 4) {
-        uint32_t id[4], wi[4];
-        Fr v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const bool on = e + k < end; id[k] = on ? __ldg(coeff_ids + e + k) : one_id; wi[k] = on ? __ldg(wire_ids + e + k) : 0xFFFFFFFFu; }
-#pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = wi[k] != 0xFFFFFFFFu ? w[wi[k]] : Fr::zero();
-#pragma unroll
-        for (int k = 0; k < 4; k++) if (wi[k] != 0xFFFFFFFFu) acc = Fr::add(acc, id[k] == one_id ? v[k] : Fr::mul(coeffs[id[k]], v[k]));
+    if (live) {
+        const uint64_t end = row_ptr[row + 1];
+        for (uint64_t e = row_ptr[row] + lane; e < end; e += ROW_LANES) {
+            const uint32_t id = __ldg(coeff_ids + e);
+            const Fr v = w[__ldg(wire_ids + e)];
+            acc = Fr::add(acc, id == one_id ? v : Fr::mul(coeffs[id], v));
+        }
     }
-    return acc;
+#pragma unroll
+    for (int off = ROW_LANES / 2; off > 0; off >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.l[i] = __shfl_down_sync(0xFFFFFFFFu, acc.l[i], off, ROW_LANES);
+        acc = Fr::add(acc, o);
+    }
+    return acc;                                            // valid on lane 0 of the group
 }
 
 __global__ void __launch_bounds__(256) k_r1cs_rows(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ wire_ids,
                                                    const uint32_t *__restrict__ coeff_ids, const Fr *__restrict__ coeffs, uint32_t one_id,
                                                    const Fr *__restrict__ w, uint64_t n_rows, Fr *__restrict__ out) {
-    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_rows) return;
-    out[row] = row_dot(row_ptr, wire_ids, coeff_ids, coeffs, one_id, w, row);
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, row = t / ROW_LANES;
+    const int lane = (int)(t % ROW_LANES);
+    const Fr acc = row_dot(row_ptr, wire_ids, coeff_ids, coeffs, one_id, w, row, row < n_rows, lane);
+    if (row < n_rows && lane == 0) out[row] = acc;
 }
 
 // j-th output = row offset + j*stride (the cyclic subsequence a rank of the distributed computeH holds); rows past the end are zero
@@ -43,17 +50,18 @@ __global__ void __launch_bounds__(256) k_r1cs_rows_strided(const uint64_t *__res
                                                            const uint32_t *__restrict__ coeff_ids, const Fr *__restrict__ coeffs, uint32_t one_id,
                                                            const Fr *__restrict__ w, uint64_t n_rows, uint64_t offset, uint64_t stride, uint64_t count,
                                                            Fr *__restrict__ out) {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, j = t / ROW_LANES;
+    const int lane = (int)(t % ROW_LANES);
     const uint64_t row = offset + j * stride;
-    out[j] = row < n_rows ? row_dot(row_ptr, wire_ids, coeff_ids, coeffs, one_id, w, row) : Fr::zero();
+    const Fr acc = row_dot(row_ptr, wire_ids, coeff_ids, coeffs, one_id, w, row, j < count && row < n_rows, lane);
+    if (j < count && lane == 0) out[j] = acc;
 }
 
 int32_t r1cs_eval_strided_dev(zkpor_ctx *ctx, zkpor_r1cs *cs, const Fr *d_wires, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t offset, uint64_t stride,
                               uint64_t count) {
     Fr *outs[3] = {d_a, d_b, d_c};
     for (int m = 0; m < 3; m++)
-        ZK_LAUNCH(ctx, k_r1cs_rows_strided, grid_for(count, 256), 256, 0, (const uint64_t *)cs->row_ptr[m], (const uint32_t *)cs->wire_ids[m],
+        ZK_LAUNCH(ctx, k_r1cs_rows_strided, grid_for(count * ROW_LANES, 256), 256, 0, (const uint64_t *)cs->row_ptr[m], (const uint32_t *)cs->wire_ids[m],
                   (const uint32_t *)cs->coeff_ids[m], (const Fr *)cs->coeffs, cs->one_id, d_wires, cs->n_rows, offset, stride, count, outs[m]);
     return ZKPOR_OK;
 }
@@ -61,7 +69,7 @@ int32_t r1cs_eval_strided_dev(zkpor_ctx *ctx, zkpor_r1cs *cs, const Fr *d_wires,
 int32_t r1cs_eval_dev(zkpor_ctx *ctx, zkpor_r1cs *cs, const Fr *d_wires, Fr *d_a, Fr *d_b, Fr *d_c) {
     Fr *outs[3] = {d_a, d_b, d_c};
     for (int m = 0; m < 3; m++)
-        ZK_LAUNCH(ctx, k_r1cs_rows, grid_for(cs->n_rows, 256), 256, 0, (const uint64_t *)cs->row_ptr[m], (const uint32_t *)cs->wire_ids[m],
+        ZK_LAUNCH(ctx, k_r1cs_rows, grid_for(cs->n_rows * ROW_LANES, 256), 256, 0, (const uint64_t *)cs->row_ptr[m], (const uint32_t *)cs->wire_ids[m],
                   (const uint32_t *)cs->coeff_ids[m], (const Fr *)cs->coeffs, cs->one_id, d_wires, cs->n_rows, outs[m]);
     return ZKPOR_OK;
 }
