@@ -1,8 +1,7 @@
 // Constraint evaluation on the GPU: a = L w, b = R w, c = O w for an R1CS whose matrices stay resident in HBM.
 // Replaces the part of gnark's r1cs.Solve (constraint/bn254/solver.go, out of tree; reached from groth16.Prove,
-// src/prover/prover/prover.go:269) that fills solution.A / .B / .C -- the wire values themselves still come from gnark's
-// solver (hints, lookups and range checks need its compiled instruction stream).
-// One thread per constraint row; a row of the reference circuits has a handful of terms, most coefficients are 1.
+// src/prover/prover/prover.go:269) that fills solution.A / .B / .C.  The wire values come from the device solver (solver.cu,
+// zkpor_groth16_prove_solve) or from the caller (zkpor_groth16_prove_wires: gnark's solver on the CPU).
 #include "internal.h"
 
 using namespace ff;
