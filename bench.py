@@ -78,6 +78,8 @@ def parse():
     ap.add_argument("--workload", default="prove", choices=["prove", "witness"],
                     help="prove: groth16.Prove (the headline metric); witness: the witness service's hot path on --accounts synthetic accounts (BASELINE config 5)")
     ap.add_argument("--accounts", type=int, default=10_000_000)
+    ap.add_argument("--tier", type=int, default=50, choices=[50, 500],
+                    help="assets per user of the circuit: 50 = zkpor50_1380 (the headline), 500 = zkpor500_200 (BASELINE config 4: ~62.9 M constraints)")
     return ap.parse_args()
 
 
@@ -187,18 +189,22 @@ FULL_CIRCUIT = dict(assets_per_user=50, cex_assets=500, tiers=12, merkle_depth=2
 CONSTRAINT_FILL = 65_000_000 / (1 << 26)         # README.md:10-21: ~65.0 M constraints on the 2^26 domain
 
 
+TIER = 50                                        # --tier: assets per user (50 -> zkpor50_1380, 500 -> zkpor500_200)
+
+
 def circuit_params(log_n):
-    """BatchCreateUser-shaped circuit for a 2^log_n domain: the per-user block is always the tier-50 one; the global parts (CEX
-    assets, the serial commitment chain) scale with the domain below 2^26; the number of users fills the domain to ~97 %."""
+    """BatchCreateUser-shaped circuit for a 2^log_n domain: the per-user block is the tier's one; the global parts (CEX
+    assets, the serial commitment chain) scale with the domain below 2^26; the number of users fills the domain to ~97 % (tier 50:
+    65.0 M constraints) / ~94 % (tier 500: 62.9 M, README.md:10-21)."""
     f = min(1.0, (1 << log_n) / (1 << 26))
-    return dict(FULL_CIRCUIT, cex_assets=max(4, int(FULL_CIRCUIT["cex_assets"] * f)), chain_perms=max(2, int(FULL_CIRCUIT["chain_perms"] * f)))
+    return dict(FULL_CIRCUIT, assets_per_user=TIER, cex_assets=max(4, int(FULL_CIRCUIT["cex_assets"] * f)), chain_perms=max(2, int(FULL_CIRCUIT["chain_perms"] * f)))
 
 
 def build_circuit(zk, log_n, xp=np, device=None):
     import importlib
     cs_mod = importlib.import_module("zkmerkle-proof-of-solvency_b200.circuit_synth")
     params = circuit_params(log_n)
-    target = int((1 << log_n) * CONSTRAINT_FILL)
+    target = int((1 << log_n) * (CONSTRAINT_FILL if TIER == 50 else 62_900_000 / (1 << 26)))
     rows = lambda cb: sum(len(s.rows) * s.count for s in cb.sections)
     r1 = rows(cs_mod.batch_create_user_like(users=1, poseidon_constants=zk.poseidon_constants, **params))
     r2 = rows(cs_mod.batch_create_user_like(users=2, poseidon_constants=zk.poseidon_constants, **params))
@@ -345,6 +351,8 @@ DTYPE = "u32 limbs (254-bit modular integers)"
 
 def main():
     args = parse()
+    global TIER
+    TIER = args.tier
     if args.workload == "witness" and args.impl == "native":
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import witness_bench
