@@ -49,7 +49,7 @@ struct DevBuf {
         if (bytes <= cap) return ZKPOR_OK;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + (bytes >> 3);
+        size_t want = bytes + (bytes < ((size_t)256 << 20) ? bytes >> 3 : 0);   // slack only where regrowth is likely: a 2^26 proof's buffers are GBs each
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
         if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); p = nullptr; return ZKPOR_ERR_OOM; }
