@@ -146,27 +146,3 @@ def test_pairing_header_matches_oracle(ht):
     want_m = pr.miller_loop(pr.untwist(qb), pr.embed_g1(pa))
     assert from_arr(mil) == want_m
     assert from_arr(gt) == pr.final_exponentiation(want_m)
-
-
-def test_split_fp2_lane_pair_formulas(ht):
-    """csrc/fp2_split.cuh (the formula text of the two-lanes-per-bucket G2 kernel) on an emulated lane pair against the
-    one-thread XYZZ<Fp2> formulas of ec.cuh: mul2, sqr, madd-2008-s and mdbl-2008-s, bit for bit."""
-    rng = SplitMix64(23)
-    for trial in range(6):
-        k1, k2, k3 = (1 + rng.field(R - 1) for _ in range(3))
-        # an accumulator in non-trivial XYZZ form: (k1 G2) + (k2 G2) accumulated with the one-thread code, then the point k3 G2
-        pts = orc.g2_pack([bn.pt_mul(G2_GEN, k1, FP2), bn.pt_mul(G2_GEN, k2, FP2), bn.pt_mul(G2_GEN, k3, FP2)])
-        acc = np.zeros(32, dtype=np.uint64)
-        o_a, o_m, o_d = np.zeros(16, dtype=np.uint64), np.zeros(16, dtype=np.uint64), np.zeros(16, dtype=np.uint64)
-        # build XYZZ(k1 G2 + k2 G2) = madd of from_affine(k1 G2) with k2 G2 via the reference ops: start from ZZ = ZZZ = 1
-        one = orc.fp_mont([1, 0])
-        start = np.concatenate([pts[0].reshape(4, 4)[:2].reshape(-1), pts[0].reshape(4, 4)[2:].reshape(-1), one.reshape(-1), one.reshape(-1)])
-        outs_ref = [np.zeros(32, dtype=np.uint64), np.zeros(32, dtype=np.uint64), np.zeros(16, dtype=np.uint64), np.zeros(8, dtype=np.uint64)]
-        ht.ht_g2_ref_ops(p(np.ascontiguousarray(start)), p(np.ascontiguousarray(pts[1])), *(p(x) for x in outs_ref))
-        acc = outs_ref[0].copy()                                   # (k1 + k2) G2 with ZZ != 1
-        ref = [np.zeros(32, dtype=np.uint64), np.zeros(32, dtype=np.uint64), np.zeros(16, dtype=np.uint64), np.zeros(8, dtype=np.uint64)]
-        got = [np.zeros(32, dtype=np.uint64), np.zeros(32, dtype=np.uint64), np.zeros(16, dtype=np.uint64), np.zeros(8, dtype=np.uint64)]
-        ht.ht_g2_ref_ops(p(acc), p(np.ascontiguousarray(pts[2])), *(p(x) for x in ref))
-        ht.ht_g2_split_ops(p(acc), p(np.ascontiguousarray(pts[2])), *(p(x) for x in got))
-        for a, b in zip(ref, got):
-            assert np.array_equal(a, b)

@@ -3,7 +3,6 @@
 // CPU against the oracle before any GPU time is spent.
 #define FF_HOST_EMULATE_PTX 1
 #include "pairing.cuh"
-#include "fp2_split.cuh"
 using namespace ff;
 using namespace ec;
 extern "C" {
@@ -69,30 +68,5 @@ void ht_fp12_ops(const uint32_t *a, const uint32_t *b, uint32_t *out_mul, uint32
     pairing::Fp12 x, y; memcpy(&x, a, 384); memcpy(&y, b, 384);
     pairing::Fp12 m = pairing::Fp12::mul(x, y), s = pairing::Fp12::sqr(x), i = pairing::Fp12::inv(x);
     memcpy(out_mul, &m, 384); memcpy(out_sqr, &s, 384); memcpy(out_inv, &i, 384);
-}
-// split-Fp2 formulas of msm_g2pair.cu on an emulated lane pair: acc (+/-) p with madd, and 2p with dbl_affine; outputs as XYZZ<Fp2>
-static fp2split::HostPair hp(const Fp2 &v) { return fp2split::HostPair{{v.a0, v.a1}}; }
-static Fp2 unhp(const fp2split::HostPair &v) { return Fp2{v.c[0], v.c[1]}; }
-void ht_g2_split_ops(const uint32_t *acc_xyzz, const uint32_t *pt, uint32_t *out_madd, uint32_t *out_dbl, uint32_t *out_mul, uint32_t *out_sqr) {
-    G2XYZZ a; G2Affine p; memcpy(&a, acc_xyzz, 256); memcpy(&p, pt, 128);
-    fp2split::HostLanes ln;
-    fp2split::Acc<fp2split::HostPair> s{hp(a.X), hp(a.Y), hp(a.ZZ), hp(a.ZZZ)};
-    fp2split::HostPair dP, dR;
-    auto r = fp2split::madd(ln, s, hp(p.x), hp(p.y), dP, dR);
-    G2XYZZ o{unhp(r.X), unhp(r.Y), unhp(r.ZZ), unhp(r.ZZZ)}; memcpy(out_madd, &o, 256);
-    auto d = fp2split::dbl_affine(ln, hp(p.x), hp(p.y));
-    G2XYZZ od{unhp(d.X), unhp(d.Y), unhp(d.ZZ), unhp(d.ZZZ)}; memcpy(out_dbl, &od, 256);
-    fp2split::HostPair z, t;
-    fp2split::mul2(ln, hp(a.X), hp(a.Y), hp(p.x), hp(p.y), z, t);
-    Fp2 zz = unhp(z), tt = unhp(t); memcpy(out_mul, &zz, 64); memcpy(out_mul + 16, &tt, 64);
-    Fp2 sq = unhp(fp2split::sqr(ln, hp(a.X))); memcpy(out_sqr, &sq, 64);
-}
-// the same through the one-thread formulas of ec.cuh (what the split form must reproduce)
-void ht_g2_ref_ops(const uint32_t *acc_xyzz, const uint32_t *pt, uint32_t *out_madd, uint32_t *out_dbl, uint32_t *out_mul, uint32_t *out_sqr) {
-    G2XYZZ a; G2Affine p; memcpy(&a, acc_xyzz, 256); memcpy(&p, pt, 128);
-    G2XYZZ m = a; m.add_affine(p, false); memcpy(out_madd, &m, 256);
-    G2XYZZ d = G2XYZZ::dbl_affine(p); memcpy(out_dbl, &d, 256);
-    Fp2 z = Fp2::mul(a.X, a.Y), t = Fp2::mul(p.x, p.y); memcpy(out_mul, &z, 64); memcpy(out_mul + 16, &t, 64);
-    Fp2 sq = Fp2::sqr(a.X); memcpy(out_sqr, &sq, 64);
 }
 }

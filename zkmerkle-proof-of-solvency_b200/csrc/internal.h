@@ -72,8 +72,6 @@ int32_t msm_view(zkpor_ctx *ctx, const MsmSorted &shared, const uint2 *wire_map,
 // when the lists are too short for it to pay (or HBM is short) and the caller must run the XYZZ accumulation instead
 int32_t msm_tree_sums(zkpor_ctx *ctx, const ec::G1Affine *d_points, const MsmSorted &s, ec::G1XYZZ *buckets, bool *done);
 int32_t msm_tree_sums(zkpor_ctx *ctx, const ec::G2Affine *d_points, const MsmSorted &s, ec::G2XYZZ *buckets, bool *done);
-// G2 bucket sums of the light buckets with two lanes per bucket (msm_g2pair.cu)
-int32_t msm_g2_pair_accumulate(zkpor_ctx *ctx, const ec::G2Affine *d_points, const MsmSorted &s, ec::G2XYZZ *buckets);
 // full device MSM on device-resident inputs; result as XYZZ on the host
 int32_t msm_g1_dev(zkpor_ctx *ctx, const void *d_points, const void *d_scalars, uint64_t n, uint32_t flags, ec::G1XYZZ *host_out);
 int32_t msm_g2_dev(zkpor_ctx *ctx, const void *d_points, const void *d_scalars, uint64_t n, uint32_t flags, ec::G2XYZZ *host_out);

@@ -149,14 +149,6 @@ __global__ void __launch_bounds__(128) k_reduce_level(const XYZZ<F> *__restrict_
     R[t] = run; An[t] = sum;
 }
 
-// ZKPOR_G2_PAIR=2|3|4 (resident CTAs per SM): a lane pair per G2 bucket (msm_g2pair.cu) instead of one thread per bucket.
-// OFF by default: correct (host-emulated formulas, oracle parity on the GPU) but measured 27 % slower than the kernel below
-// (DESIGN.md 6b).
-static bool g2_pair_lanes() {
-    static const bool on = [] { const char *v = getenv("ZKPOR_G2_PAIR"); return v != nullptr && atoi(v) >= 2; }();
-    return on;
-}
-
 template <class F>
 static int32_t msm_accumulate(zkpor_ctx *ctx, const void *d_points, const MsmSorted &s, XYZZ<F> *host_out, uint64_t terms = 0) {
     const MsmPlan plan = s.plan;
@@ -169,11 +161,8 @@ static int32_t msm_accumulate(zkpor_ctx *ctx, const void *d_points, const MsmSor
         bool done = false;
         if (!s.is_view) ZK_TRY(msm_tree_sums(ctx, (const Affine<F> *)d_points, s, ctx->buckets.as<XYZZ<F>>(), &done));
         if (!done) {
-            if (sizeof(F) != sizeof(Fp) && g2_pair_lanes())
-                ZK_TRY(msm_g2_pair_accumulate(ctx, (const G2Affine *)d_points, s, ctx->buckets.as<G2XYZZ>()));
-            else
-                ZK_LAUNCH(ctx, (k_accumulate<F>), grid_for(slots, 128), 128, 0, (const Affine<F> *)d_points, s.idx, s.off, s.cnt, s.n, plan, s.heavy_t,
-                          s.order, ctx->buckets.as<XYZZ<F>>());
+            ZK_LAUNCH(ctx, (k_accumulate<F>), grid_for(slots, 128), 128, 0, (const Affine<F> *)d_points, s.idx, s.off, s.cnt, s.n, plan, s.heavy_t,
+                      s.order, ctx->buckets.as<XYZZ<F>>());
         }
         ZK_TRY(ctx->heavy_part.reserve((size_t)s.max_blks * sizeof(XYZZ<F>)));
         ZK_LAUNCH(ctx, (k_accumulate_heavy<F>), (s.max_blks < 8u * ctx->sm_count ? s.max_blks : 8u * ctx->sm_count), 128, 0, (const Affine<F> *)d_points, s.idx, s.blks, s.counters, s.n, plan,
