@@ -47,6 +47,33 @@ def test_null_arguments_of_the_newer_entry_points():
         assert lib.zkpor_last_error()
 
 
+def test_null_arguments_of_the_round2_entry_points():
+    """solver, sharded proof, containers, witness batches: a null handle is ZKPOR_ERR_INVALID_ARG with a message, never a crash"""
+    lib = zk.lib()
+    for call in (lambda: lib.zkpor_program_upload(None, None, None),
+                 lambda: lib.zkpor_program_stats(None, None),
+                 lambda: lib.zkpor_program_tail_info(None, None),
+                 lambda: lib.zkpor_program_tail_wires(None, None, 0),
+                 lambda: lib.zkpor_program_r1cs(None, None),
+                 lambda: lib.zkpor_r1cs_solve(None, None, None, None, None, None, None, None, None),
+                 lambda: lib.zkpor_groth16_prove_solve(None, None, None, None, None, None, None, None),
+                 lambda: lib.zkpor_pk_upload_shard(None, None, None),
+                 lambda: lib.zkpor_pk_shard_info(None, None),
+                 lambda: lib.zkpor_proof_decode(None, None, 0, None, None, None),
+                 lambda: lib.zkpor_proof_encode(None, None, 0, 1, None, None),
+                 lambda: lib.zkpor_vk_decode(None, None, 0, None, None, 0, None, 0, None),
+                 lambda: lib.zkpor_vk_encode(None, None, None, None, 0, None, 0, None),
+                 lambda: lib.zkpor_pk_read(None, None, 0, None, None, None),
+                 lambda: lib.zkpor_pk_write(None, None, 0, None, 0, None),
+                 lambda: lib.zkpor_g1_encode_batch(None, None, 1, 1, None),
+                 lambda: lib.zkpor_witness_batches(None, None, None, None, None, 0, 50, 1380, None, None, None),
+                 lambda: lib.zkpor_tree_build_sharded(None, None),
+                 lambda: lib.zkpor_tree_shard_range(None, None, None, None, None)):
+        assert call() == 1
+        assert lib.zkpor_last_error()
+    assert lib.zkpor_program_free(None, None) == 0
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
