@@ -172,3 +172,15 @@ def test_point_encode_batch_is_the_inverse_of_decode(ctx):
         zk._check(zk.lib().zkpor_g2_encode_batch(ctx._h, zk._ptr(p2), len(g2), comp, zk._ptr(enc)))
         assert enc.tobytes() == b"".join((bn.g2_compressed_bytes if comp else bn.g2_raw_bytes)(p) for p in g2)
         assert np.array_equal(ctx.g2_decode_batch(enc, len(g2), bool(comp)), p2)
+
+
+def test_containers_against_the_committed_fixture(ctx):
+    """tests/golden/containers.json: committed bytes of a seeded instance (made by tests/golden/make_containers.py from the oracle)"""
+    import json
+    import os
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "containers.json")))
+    comp, raw = bytes.fromhex(fx["proof_compressed"]), bytes.fromhex(fx["proof_raw"])
+    assert zk.proof_decode(ctx, comp) == raw and zk.proof_encode(ctx, raw, compressed=True) == comp
+    vkb = bytes.fromhex(fx["vk_compressed"])
+    vk = zk.vk_decode(ctx, vkb)
+    assert vk["bytes_consumed"] == 524 and zk.vk_encode(ctx, vk) == vkb

@@ -6,6 +6,7 @@ The fixture is copied (data only) to tests/golden/user_config_proof.json by test
 import base64
 import json
 import os
+import sys
 
 import bn254 as bn
 import merkle
@@ -216,3 +217,13 @@ def test_container_sizes_match_the_reference_key_files():
     # the proving key: both encodings parse back to the same arrays, and the header names the domain
     kb = ct.pk_bytes(pk)
     assert int.from_bytes(kb[:8], "big") == pk["domain"].n and len(ct.pk_bytes(pk, raw=True)) > len(kb)
+
+
+def test_container_bytes_match_the_committed_fixture():
+    """tests/golden/containers.json (made by tests/golden/make_containers.py) freezes the restated layouts: a change of
+    oracle/py/containers.py shows up here as a byte diff."""
+    sys.path.insert(0, GOLDEN)
+    import make_containers
+    want = json.load(open(os.path.join(GOLDEN, "containers.json")))
+    assert make_containers.build() == want
+    assert len(bytes.fromhex(want["vk_compressed"])) == 524 and len(bytes.fromhex(want["proof_raw"])) == 388
